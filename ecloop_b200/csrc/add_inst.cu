@@ -1,0 +1,23 @@
+// add_inst.cu — one add_kernel variant per translation unit (-DADD_VARIANT=0..5) so the six address-type /
+// endomorphism combinations compile in parallel. Variant = (A33 ? 1 : 0) | (A65 ? 2 : 0) | (ENDO ? 4 : 0), minus 1
+// for the two invalid "no address type" codes (see add_variant_index in ecl_api.cu).
+#include <cuda_runtime.h>
+
+#include "add_kernel.cuh"
+
+#ifndef ADD_VARIANT
+#error "compile with -DADD_VARIANT=<flags 1..3 or 5..7>"
+#endif
+#define V_A33 ((ADD_VARIANT & 1) != 0)
+#define V_A65 ((ADD_VARIANT & 2) != 0)
+#define V_ENDO ((ADD_VARIANT & 4) != 0)
+#define CAT2(a, b) a##b
+#define CAT(a, b) CAT2(a, b)
+
+cudaError_t CAT(ecl_add_launch_, ADD_VARIANT)(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
+  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fn<<<grid, ADD_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}

@@ -1,0 +1,116 @@
+// add_kernel.cuh — K1, the fused add kernel: batch_add + check_found_add + addr33/65_batch + blf_has
+// (main.c:287-403, lib/addr.c:99-131, lib/utils.c:308-326) in one launch.
+#pragma once
+#include "common.cuh"
+
+struct AddParams {
+  const u32 *cx, *cy;  // thread centres, SoA: limb l of thread t at [l*T + t]
+  const uint4 *table;  // H+1 affine points of 64 B: entry i<H = (i+1)*s*G, entry H = 2H*s*G (group step)
+  uint4 *scratch;      // prefix products: element i, half h of thread t at [(2i+h)*T + t]
+  BloomView bloom;     // device-global filter
+  u32 bloom_smem_words;  // != 0: the filter is staged into shared memory (then == bloom.size)
+  HitSink sink;
+  u32 T;                  // threads that own work (also the SoA stride)
+  u32 groups_per_thread;  // consecutive groups of 2H keys owned by one thread
+  u64 n_groups;           // groups in this launch
+  u64 key_off0;           // index (in keys) of the first key of this launch inside the submitted span
+};
+
+// Thread t owns the consecutive groups [t*c, (t+1)*c) of 2H keys. For one group with centre point
+// P = (start + (g*2H + H)*s)*G it forms every P +- (i+1)*s*G, i < H, sharing ONE field inversion through
+// Montgomery's trick (fe_modp_grpinv, lib/ecc.c:522-540): prefix products go to a coalesced global scratch
+// (32 B per element, written once, read once), the running inverse stays in registers. The group step 2H*s*G
+// rides in the same batch as element 0, so moving to the next group costs one affine addition and no
+// extra inversion (the reference pays a second inversion per group for that, main.c:400).
+// Key order inside a group matches the reference: K-H .. K-1, K, K+1 .. K+H-1 (main.c:363,391).
+template <int H, bool A33, bool A65, bool ENDO>
+__global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const AddParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) u64 mbar;
+  uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
+  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw + (H + 1) * 64);
+  const u32 tab_bytes = (H + 1) * 64;
+  const u32 bloom_bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;
+
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&mbar, tab_bytes + bloom_bytes);
+    bulk_g2s(tab, p.table, tab_bytes, &mbar);
+    if (bloom_bytes) bulk_g2s(sbloom, p.bloom.bits, bloom_bytes, &mbar);
+  }
+  mbar_wait(&mbar, 0);
+
+  BloomView bv = p.bloom;
+  if (p.bloom_smem_words) bv.bits = sbloom;
+
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.T) return;
+  const u32 T = p.T;
+
+  fe px, py;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
+
+  const u64 g0 = (u64)t * p.groups_per_thread;
+  u64 g1 = g0 + p.groups_per_thread;
+  if (g1 > p.n_groups) g1 = p.n_groups;
+  uint4 *scr = p.scratch + t;
+
+#pragma unroll 1
+  for (u64 g = g0; g < g1; ++g) {
+    const u64 kc = p.key_off0 + g * (2 * H) + H;  // key index of the centre
+
+    // ---- pass 1: prefix products e_0, e_0 e_1, ...   e_0 = step.x - px, e_{i+1} = table[i].x - px
+    fe acc = fe_sub(fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]), px);
+#pragma unroll 1
+    for (int i = 0; i < H; ++i) {
+      scr[(size_t)(2 * i) * T] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      scr[(size_t)(2 * i + 1) * T] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+      const fe d = fe_sub(fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]), px);
+      acc = fe_mul(acc, d);
+    }
+    fe inv = fe_inv(acc);  // 1 / (e_0 ... e_H)
+
+    // ---- pass 2: peel the inverses off from the far end; two points per step
+#pragma unroll 1
+    for (int i = H - 1; i >= 0; --i) {
+      const fe pre = fe_from_u4(scr[(size_t)(2 * i) * T], scr[(size_t)(2 * i + 1) * T]);  // e_0 ... e_i
+      const fe gx = fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]);
+      const fe gy = fe_from_u4(tab[i * 4 + 2], tab[i * 4 + 3]);
+      const fe inv_i = fe_mul(inv, pre);  // 1 / (gx - px)
+      inv = fe_mul(inv, fe_sub(gx, px));  // 1 / (e_0 ... e_i)
+
+      u32 x[2][8], y[2][8];
+      u64 off[2];
+      fe rx, ry;
+      // lane 0: P - (i+1)sG  -> key K - (i+1)
+      affine_add_inv(rx, ry, px, py, gx, fe_neg(gy), inv_i);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) x[0][l] = rx.v[l], y[0][l] = ry.v[l];
+      off[0] = kc - (u64)(i + 1);
+      // lane 1: P + (i+1)sG -> key K + (i+1); the far end K+H is outside the group, its slot takes K itself
+      if (i == H - 1) {
+        rx = px, ry = py;
+        off[1] = kc;
+      } else {
+        affine_add_inv(rx, ry, px, py, gx, gy, inv_i);
+        off[1] = kc + (u64)(i + 1);
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) x[1][l] = rx.v[l], y[1][l] = ry.v[l];
+
+      check_points<2, A33, A65, ENDO>(bv, p.sink, x, y, off);
+    }
+
+    // ---- next group's centre: P + 2H*s*G with inv = 1/(step.x - px)
+    {
+      const fe sx = fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]);
+      const fe sy = fe_from_u4(tab[H * 4 + 2], tab[H * 4 + 3]);
+      fe nx, ny;
+      affine_add_inv(nx, ny, px, py, sx, sy, inv);
+      px = nx, py = ny;
+    }
+  }
+}
+

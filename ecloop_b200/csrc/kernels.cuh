@@ -1,0 +1,166 @@
+// kernels.cuh — the small sm_100a kernels behind the C-ABI (the fused add kernel lives in add_kernel.cuh and is
+// compiled one variant per translation unit, add_inst.cu):
+//
+//   mul_kernel<A33,A65>          K2: ec_gtable_mul + normalise + hash160 + blf_has (main.c:531-534)
+//   smul_kernel                  K3: k*G for generated or given scalars -> +-i*s*G table / thread centres
+//                                (ctx_precompute_gpoints main.c:219-246, GStart main.c:359-360)
+//   gtab_bases/gtab_fill         one-off window table d * 2^(16 w) * G (ec_gtable_init, lib/ecc.c:880-905)
+//   prim_* kernels               per-routine parity entry points
+#pragma once
+#include "add_kernel.cuh"
+#include "common.cuh"
+
+// ---------------------------------------------------------------- K3: scalar multiples of G
+
+struct SmulParams {
+  fe k0, step;         // generated scalars: k = k0 + m(j)*step (mod n)
+  const fe *scalars;   // mode 2: explicit scalars instead
+  const uint4 *gtab;
+  u32 count;
+  u32 mode;  // 0: add-kernel table (m = j+1 for j < count-1, m = 2*(count-1) for the last = group step), AoS out
+             // 1: thread centres (m = j), SoA out with stride `count`
+             // 2: explicit scalars, AoS out (zeros for the point at infinity)
+  u32 *out;
+};
+
+__global__ void __launch_bounds__(128) smul_kernel(const SmulParams p) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.count) return;
+  fe k;
+  if (p.mode == 2) k = p.scalars[j];
+  else {
+    u32 m = j;
+    if (p.mode == 0) m = (j + 1 < p.count) ? j + 1 : 2 * (p.count - 1);
+    k = sc_muladd_small(p.k0, p.step, m);
+  }
+  jac a;
+  fe x = fe_zero(), y = fe_zero();
+  if (gtab_mul(a, k, p.gtab)) jac_to_affine(x, y, a);
+  if (p.mode == 1) {
+    for (int l = 0; l < 8; ++l) p.out[(size_t)l * p.count + j] = x.v[l], p.out[(size_t)(8 + l) * p.count + j] = y.v[l];
+  } else {
+    for (int l = 0; l < 8; ++l) p.out[(size_t)j * 16 + l] = x.v[l], p.out[(size_t)j * 16 + 8 + l] = y.v[l];
+  }
+}
+
+// ---------------------------------------------------------------- K2: mul path
+
+struct MulParams {
+  const fe *scalars;
+  const uint4 *gtab;
+  BloomView bloom;
+  HitSink sink;
+  u32 count;
+};
+
+template <bool A33, bool A65>
+__global__ void __launch_bounds__(128) mul_kernel(const MulParams p) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.count) return;
+  const fe k = p.scalars[j];
+  jac a;
+  if (!gtab_mul(a, k, p.gtab)) return;  // k = 0 (mod n): no public key
+  fe fx, fy;
+  jac_to_affine(fx, fy, a);
+  u32 x[1][8], y[1][8];
+  for (int l = 0; l < 8; ++l) x[0][l] = fx.v[l], y[0][l] = fy.v[l];
+  const u64 off[1] = {j};
+  check_points<1, A33, A65, false>(p.bloom, p.sink, x, y, off);
+}
+
+// ---------------------------------------------------------------- window table build (one-off per device)
+
+// bases[w] = 2^(16 w) * G, affine (16 threads)
+__global__ void gtab_bases_kernel(u32 *bases) {
+  const u32 w = threadIdx.x;
+  if (w >= GTAB_WINDOWS) return;
+  jac a;
+  a.x.v[0] = 0x16f81798u, a.x.v[1] = 0x59f2815bu, a.x.v[2] = 0x2dce28d9u, a.x.v[3] = 0x029bfcdbu;
+  a.x.v[4] = 0xce870b07u, a.x.v[5] = 0x55a06295u, a.x.v[6] = 0xf9dcbbacu, a.x.v[7] = 0x79be667eu;
+  a.y.v[0] = 0xfb10d4b8u, a.y.v[1] = 0x9c47d08fu, a.y.v[2] = 0xa6855419u, a.y.v[3] = 0xfd17b448u;
+  a.y.v[4] = 0x0e1108a8u, a.y.v[5] = 0x5da4fbfcu, a.y.v[6] = 0x26a3c465u, a.y.v[7] = 0x483ada77u;
+  a.z = fe_one();
+  for (u32 i = 0; i < w * GTAB_W; ++i) {
+    jac t;
+    jac_dbl(t, a);
+    a = t;
+  }
+  fe x, y;
+  jac_to_affine(x, y, a);
+  for (int l = 0; l < 8; ++l) bases[w * 16 + l] = x.v[l], bases[w * 16 + 8 + l] = y.v[l];
+}
+
+// gtab[w*65535 + d-1] = d * bases[w], d = 1..65535, by left-to-right double-and-add, then normalised
+__global__ void __launch_bounds__(128) gtab_fill_kernel(u32 *gtab, const u32 *bases) {
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= GTAB_ENTRIES) return;
+  const u32 w = idx / GTAB_PER_WIN, d = idx % GTAB_PER_WIN + 1;
+  fe bx, by;
+  for (int l = 0; l < 8; ++l) bx.v[l] = bases[w * 16 + l], by.v[l] = bases[w * 16 + 8 + l];
+  jac a;
+  bool have = false;
+  for (int bit = GTAB_W - 1; bit >= 0; --bit) {
+    if (have) {
+      jac t;
+      jac_dbl(t, a);
+      a = t;
+    }
+    if ((d >> bit) & 1) {
+      if (!have) {
+        a.x = bx, a.y = by, a.z = fe_one();
+        have = true;
+      } else {
+        jac t;
+        jac_madd(t, a, bx, by);
+        a = t;
+      }
+    }
+  }
+  fe x, y;
+  jac_to_affine(x, y, a);
+  for (int l = 0; l < 8; ++l) gtab[(size_t)idx * 16 + l] = x.v[l], gtab[(size_t)idx * 16 + 8 + l] = y.v[l];
+}
+
+// ---------------------------------------------------------------- primitive parity kernels
+
+__global__ void prim_fp_kernel(int op, const fe *a, const fe *b, fe *out, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fe x = a[i];
+  fe y = fe_zero();
+  if (b) y = b[i];
+  fe r;
+  switch (op) {
+  case ECL_OP_MUL: r = fe_mul(x, y); break;
+  case ECL_OP_SQR: r = fe_sqr(x); break;
+  case ECL_OP_ADD: r = fe_add(x, y); break;
+  case ECL_OP_SUB: r = fe_sub(x, y); break;
+  case ECL_OP_NEG: r = fe_neg(x); break;
+  default: r = fe_inv(x); break;
+  }
+  out[i] = r;
+}
+
+__global__ void prim_hash160_kernel(const u32 *xy, u32 *out33, u32 *out65, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x[1][8], y[1][8];
+  for (int l = 0; l < 8; ++l) x[0][l] = xy[(size_t)i * 16 + l], y[0][l] = xy[(size_t)i * 16 + 8 + l];
+  vw<1> h[5];
+  if (out33) {
+    const u32 odd[1] = {y[0][0]};
+    hash160_33<1>(h, x, odd);
+    for (int k = 0; k < 5; ++k) out33[(size_t)i * 5 + k] = h[k].l[0];
+  }
+  if (out65) {
+    hash160_65<1>(h, x, y);
+    for (int k = 0; k < 5; ++k) out65[(size_t)i * 5 + k] = h[k].l[0];
+  }
+}
+
+__global__ void prim_bloom_kernel(BloomView bv, const u32 *h160, uint8_t *out, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 hh[5] = {h160[i * 5], h160[i * 5 + 1], h160[i * 5 + 2], h160[i * 5 + 3], h160[i * 5 + 4]};
+  out[i] = bloom_has(bv, hh) ? 1 : 0;
+}

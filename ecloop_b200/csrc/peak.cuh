@@ -1,0 +1,47 @@
+// peak.cuh — integer-pipe throughput microbenchmarks (build-plan step 0b).
+// The fused add kernel is bound by the SM's integer ALU pipe (LOP3 / SHF / IADD3), not by HBM or the tensor
+// cores, so the roofline denominator has to be measured: each kernel below issues ITER x UNROLL x 8 independent
+// chains of ONE instruction kind from every resident warp of every SM; ops/s = lanes * instructions / time.
+// The instruction mix is pinned with inline PTX that ptxas maps 1:1 (lop3.b32 -> LOP3.LUT, shf.l.wrap -> SHF,
+// mad.lo.u32 -> IMAD, mad.wide.u32 -> IMAD.WIDE.U32); profiles/ holds the SASS check.
+#pragma once
+#include <stdint.h>
+
+#define PEAK_ITERS 4096
+#define PEAK_CHAINS 8
+#define PEAK_UNROLL 4
+
+template <int KIND>
+__global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
+  uint32_t r[PEAK_CHAINS];
+  uint64_t q[PEAK_CHAINS];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) r[c] = seed * (c + 1) + t, q[c] = (uint64_t)r[c] << 7;
+  const uint32_t m = seed | 1u, z = seed ^ 0x9e3779b9u;
+  const long long c0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+    for (int u = 0; u < PEAK_UNROLL; ++u) {
+#pragma unroll
+      for (int c = 0; c < PEAK_CHAINS; ++c) {
+        if (KIND == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+        if (KIND == 1) asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(r[c]) : "r"(m), "r"(z));  // one IADD3
+        if (KIND == 2) asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(r[c]));
+        if (KIND == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(m), "r"(z));
+        if (KIND == 4) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(q[c]) : "r"(r[c]), "r"(m));
+        if (KIND == 5) {  // half the chains on the ALU pipe, half on the FMA pipe: do they co-issue?
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(m), "r"(z));
+        }
+      }
+    }
+  }
+  const long long c1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) acc ^= r[c] ^ (uint32_t)q[c] ^ (uint32_t)(q[c] >> 32);
+  if (acc == 0x12345678u) out[t & 1023] = acc;  // keep the chains alive
+  if (t == 0) *cycles = (unsigned long long)(c1 - c0);
+}

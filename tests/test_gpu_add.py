@@ -1,0 +1,212 @@
+"""GPU parity of the fused add path (ecl_add_submit/ecl_collect) against the reference's known answers, the
+reference binary's full dumps (tests/golden) and the oracle on seeded inputs. Bit-exact."""
+import ctypes as C
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import GOLD, golden_lines
+
+pytestmark = pytest.mark.gpu
+N = O.N_ORDER
+
+
+@pytest.fixture(scope="module")
+def E():
+    import ecloop_b200
+
+    return ecloop_b200
+
+
+@pytest.fixture(scope="module")
+def dev(E):
+    d = E.Device(0)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def H():
+    import ecloop_b200.host as host
+
+    return host
+
+
+def sha_lines(lines):
+    return hashlib.sha256(("\n".join(lines) + "\n").encode()).hexdigest()
+
+
+def all_ones(H):
+    return H.Filter(np.full(1, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64), None)
+
+
+# ---------------------------------------------------------------- the reference's own known answers
+
+
+def test_ci_smoke_range(dev, H, E, golden):
+    s = H.Searcher(dev, H.load_filter(GOLD / "btc-puzzles-hash"), E.A33)
+    found = s.cmd_add(0x8000, 0xFFFF)
+    assert [f.line() for f in found] == golden_lines("ka_add_8000_ffff")
+    assert s.k_checked == 32767
+
+
+def test_make_add_9_keys(dev, H, E, golden):
+    s = H.Searcher(dev, H.load_filter(GOLD / "btc-puzzles-hash"), E.A33)
+    found = s.cmd_add(0x8000, 0xFFFFFF)
+    lines = sorted(f.line() for f in found)
+    assert len(lines) == 9 and s.k_checked == 16777216
+    assert hashlib.md5(("\n".join(lines) + "\n").encode()).hexdigest() == "6309efbef3fda727aac597db3a7f1a27"
+    assert lines == sorted(golden_lines("ka_add_8000_ffffff"))
+
+
+def test_13_keys_2p28(dev, H, E):
+    s = H.Searcher(dev, H.load_filter(GOLD / "btc-puzzles-hash"), E.A33)
+    found = s.cmd_add(0x8000, 0xFFFFFFF)
+    assert sorted(f.line() for f in found) == sorted(golden_lines("ka_add_8000_fffffff"))
+    assert s.k_checked == 268435456
+
+
+def test_70bit_window(dev, H, E):
+    s = H.Searcher(dev, H.load_filter(GOLD / "btc-puzzles-hash"), E.A33)
+    found = s.cmd_add(0x349B84B6431A000000, 0x349B84B6431AFFFFFF)
+    assert [f.line() for f in found] == golden_lines("ka_add_70bit")
+
+
+# ---------------------------------------------------------------- full dumps of the reference binary
+
+
+def run_dump(dev, H, flags, range_s, range_e, offs=0):
+    s = H.Searcher(dev, all_ones(H), flags)
+    found = s.cmd_add(range_s, range_e, offs)
+    return [f.line() for f in found], s
+
+
+def check_dump(golden, name, lines):
+    m = golden[name]
+    assert len(lines) == m["n_lines"]
+    assert lines[:16] == m["head"]
+    assert lines[-16:] == m["tail"]
+    assert sha_lines(lines) == m["sha256_emission_order"]
+
+
+def test_dump_cu(dev, H, E, golden):
+    lines, _ = run_dump(dev, H, E.A33 | E.A65, 0x8000, 0x8007)
+    assert lines == golden_lines("dump_add_8000_cu")
+
+
+def test_dump_u_only(dev, H, E):
+    lines, _ = run_dump(dev, H, E.A65, 0x8000, 0x8007)
+    assert lines == [l for l in golden_lines("dump_add_8000_cu") if l.startswith("addr65")]
+
+
+def test_dump_endo(dev, H, E, golden):
+    lines, s = run_dump(dev, H, E.A33 | E.ENDO, 0x8000, 0x8007)
+    check_dump(golden, "dump_add_8000_endo_c", lines)
+    assert s.k_checked == 7 * 6
+    lines, _ = run_dump(dev, H, E.A33 | E.A65 | E.ENDO, 0x8000, 0x8007)
+    check_dump(golden, "dump_add_8000_endo_cu", lines)
+    lines65, _ = run_dump(dev, H, E.A65 | E.ENDO, 0x8000, 0x8007)
+    assert lines65 == [l for l in lines if l.startswith("addr65")]
+
+
+def test_dump_2p70_and_stride(dev, H, E, golden):
+    lines, _ = run_dump(dev, H, E.A33, 2**70, 2**70 + 7)
+    check_dump(golden, "dump_add_2p70_c", lines)
+    lines, _ = run_dump(dev, H, E.A33 | E.A65, 2**70, 2**70 + 7, offs=7)
+    check_dump(golden, "dump_add_2p70_stride7_cu", lines)
+
+
+def test_dump_multi_group_overshoot(dev, H, E, golden):
+    lines, s = run_dump(dev, H, E.A33, 0x8000, 0x9FFF)
+    check_dump(golden, "dump_add_multi_group", lines)
+    assert s.k_checked == 0x1FFF
+
+
+def test_dump_two_jobs_4m_lines(dev, H, E, golden):
+    # 2 reference jobs of 2^21 keys; also drives the hit-ring overflow path (4.2 M hits > ring capacity)
+    lines, s = run_dump(dev, H, E.A33, 0x10000, 0x40FFFF)
+    check_dump(golden, "dump_add_2jobs", lines)
+    assert s.k_checked == 2 * 2**21
+
+
+def test_small_hit_ring_is_exact(dev, H, E):
+    dev.set_tuning(0, 12 * 2048)
+    try:
+        lines, _ = run_dump(dev, H, E.A33 | E.A65, 0x8000, 0x8007)
+        assert lines == golden_lines("dump_add_8000_cu")
+    finally:
+        dev.set_tuning(0, 0)
+
+
+# ---------------------------------------------------------------- against the oracle on seeded inputs
+
+
+def sparse_filter(H, seed, size_words, fill):
+    """a bloom with a given fill: exercises deep probe chains and false positives, which must match bit for bit"""
+    rng = np.random.default_rng(seed)
+    bits = np.zeros(size_words, dtype=np.uint64)
+    for b in range(64):
+        bits |= (rng.random(size_words) < fill).astype(np.uint64) << np.uint64(b)
+    return H.Filter(bits, None)
+
+
+@pytest.mark.parametrize("seed,flags_name,offs", [(1, "c", 0), (2, "cu", 0), (3, "c_endo", 0), (4, "cu_endo", 5), (5, "u", 13)])
+def test_random_spans_vs_oracle(dev, H, E, seed, flags_name, offs):
+    flags = {"c": E.A33, "u": E.A65, "cu": E.A33 | E.A65, "c_endo": E.A33 | E.ENDO, "cu_endo": E.A33 | E.A65 | E.ENDO}[flags_name]
+    r = random.Random(seed)
+    flt = sparse_filter(H, seed, 1021, 0.80)  # 0.8^20 ~ 1.2 % of hashes pass all 20 probes
+    bits_c = (C.c_uint64 * flt.bits.size)(*[int(x) for x in flt.bits])
+    oflt = O.HostFilter(bits_c, flt.bits.size, None)
+    dev.set_filter(flt.bits)
+    dev.set_stride(1 << offs)
+    for n_keys in (2048, 6144, 32768):
+        start = r.getrandbits(r.choice([20, 71, 130, 255])) + 4096
+        got = dev.batch_add(start, n_keys, flags)
+        n, want = O.add_span(start, 1 << offs, n_keys, flags, oflt)
+        assert n == len(want)
+        assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
+        # and the recovered keys
+        for (k, e, kd, h), w in list(zip(got, want))[:50]:
+            assert H.calc_priv(start, 1 << offs, k, e) == w[4]
+    dev.set_stride(1)
+
+
+def test_many_threads_ragged_tail(dev, H, E):
+    """spans that do not divide evenly over threads / launches: every key reported exactly once"""
+    flt = sparse_filter(H, 9, 509, 0.85)
+    dev.set_filter(flt.bits)
+    bits_c = (C.c_uint64 * flt.bits.size)(*[int(x) for x in flt.bits])
+    oflt = O.HostFilter(bits_c, flt.bits.size, None)
+    dev.set_tuning(1, 0)  # one group per thread -> several launches for a modest span
+    try:
+        start = 2**70 + 12345
+        n_keys = 2048 * 151
+        got = dev.batch_add(start, n_keys, E.A33)
+        n, want = O.add_span(start, 1, n_keys, O.A33, oflt)
+        assert [(k, "".join("%08x" % w for w in h)) for k, _, _, h in got] == [(k, h) for k, _, _, h, _ in want]
+    finally:
+        dev.set_tuning(0, 0)
+
+
+# ---------------------------------------------------------------- size-independent properties at full size
+
+
+def test_planted_keys_full_size(dev, H, E):
+    """BASELINE config 2 shape: 2^70 + [0, 2^34) with planted hashes. Every planted key and nothing else."""
+    r = random.Random(71)
+    span = 2**34
+    offs = sorted(r.randrange(span) for _ in range(48)) + [0, span - 1]
+    keys = [2**70 + o for o in offs]
+    info = O.pubkey_hashes(keys)
+    puzzle = [l.strip() for l in open(GOLD / "btc-puzzles-hash") if len(l.strip()) == 40]
+    flt = H.filter_from_hashes(puzzle + [h33 for _, _, h33, _ in info])
+    s = H.Searcher(dev, flt, E.A33)
+    found = s.cmd_add(2**70, 2**70 + span)
+    assert sorted(f.pk for f in found) == sorted(keys)
+    assert s.k_checked == span
+    byk = {f.pk: f for f in found}
+    for k, (_, _, h33, _) in zip(keys, info):
+        assert "".join("%08x" % w for w in byk[k].h160) == h33
