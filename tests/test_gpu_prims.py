@@ -136,4 +136,4 @@ def test_bloom(dev, size):
     got = dev.bloom_has(probes)
     want = [bool(O.lib().orc_blf_has(bits, C.c_uint64(size), (C.c_uint32 * 5)(*h))) for h in probes]
     assert got == want
-    assert all(got[:500])
+    assert all(got[: len(members[:500])])  # no false negatives
