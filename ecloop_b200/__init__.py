@@ -10,6 +10,7 @@ checked), but opening a device without CUDA raises EclError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import build as _build
@@ -51,11 +52,17 @@ def load_library(rebuild: bool = False) -> C.CDLL:
     if _lib is not None and not rebuild:
         return _lib
     path = _build.OUT
-    try:
-        path = _build.build()
-    except Exception as e:  # no nvcc on this box: use the prebuilt library that travelled with the repo
+    override = os.environ.get("ECLOOP_B200_LIB")  # tuning variants (tools/build_variants.py); never a fallback
+    if override:
+        path = Path(override)
         if not path.exists():
-            raise EclError(-1, f"libecloop_b200.so is missing and cannot be built here: {e}") from e
+            raise EclError(-1, f"ECLOOP_B200_LIB={override} does not exist")
+    else:
+        try:
+            path = _build.build()
+        except Exception as e:  # no nvcc on this box: use the prebuilt library that travelled with the repo
+            if not path.exists():
+                raise EclError(-1, f"libecloop_b200.so is missing and cannot be built here: {e}") from e
     lib = C.CDLL(str(path))
     lib.ecl_last_error.restype = C.c_char_p
     lib.ecl_last_error.argtypes = [C.c_void_p]

@@ -43,8 +43,19 @@ def _sources_hash(extra: str = "") -> str:
     return h.hexdigest()[:16]
 
 
-def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = ()) -> Path:
-    """Compile (if stale) and return the path of libecloop_b200.so."""
+def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), variant: str | None = None) -> Path:
+    """Compile (if stale) and return the path of libecloop_b200.so. `variant` builds a tuning variant with the
+    given -D defines into build/variants/libecloop_b200_<variant>.so (tools/build_variants.py)."""
+    global OUT, OBJ
+    if variant:
+        out, obj = ROOT / "build" / "variants" / f"libecloop_b200_{variant}.so", ROOT / "build" / f"obj_{variant}"
+        saved = (OUT, OBJ)
+        OUT, OBJ = out, obj
+        try:
+            out.parent.mkdir(parents=True, exist_ok=True)
+            return build(force, verbose, defines)
+        finally:
+            OUT, OBJ = saved
     tag = _sources_hash(" ".join(defines))
     stamp = OBJ / "stamp.txt"
     if not force and OUT.exists() and stamp.exists() and stamp.read_text() == tag:

@@ -56,6 +56,11 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
   u64 g1 = g0 + p.groups_per_thread;
   if (g1 > p.n_groups) g1 = p.n_groups;
   uint4 *scr = p.scratch + t;
+#ifdef ECL_LOCKSTEP
+  // every thread of this CTA walks the same number of groups: the warps may re-align at a barrier once per
+  // pass-2 step so that they fetch the (large, fully unrolled) hash code together
+  const bool lockstep = (u64)(blockIdx.x + 1) * blockDim.x * p.groups_per_thread <= p.n_groups;
+#endif
 
 #pragma unroll 1
   for (u64 g = g0; g < g1; ++g) {
@@ -75,6 +80,9 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
     // ---- pass 2: peel the inverses off from the far end; two points per step
 #pragma unroll 1
     for (int i = H - 1; i >= 0; --i) {
+#ifdef ECL_LOCKSTEP
+      if (lockstep && (i % ECL_LOCKSTEP) == 0) __syncthreads();
+#endif
       const fe pre = fe_from_u4(scr[(size_t)(2 * i) * T], scr[(size_t)(2 * i + 1) * T]);  // e_0 ... e_i
       const fe gx = fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]);
       const fe gy = fe_from_u4(tab[i * 4 + 2], tab[i * 4 + 3]);

@@ -7,8 +7,12 @@
 #include "fp.cuh"
 #include "hash160.cuh"
 
+#ifndef ADD_THREADS
 #define ADD_THREADS 256
+#endif
+#ifndef ADD_MIN_BLOCKS
 #define ADD_MIN_BLOCKS 2
+#endif
 #ifndef ADD_H
 #define ADD_H 1024  // half group: 2*ADD_H keys share one inversion; 2048 = the reference's GROUP_INV_SIZE
 #endif

@@ -76,6 +76,80 @@ __device__ __forceinline__ vw<N> vset(u32 c) {
   return r;
 }
 
+
+// ---------------------------------------------------------------- pipe steering
+// The fused add kernel is bound by the ALU pipe (LOP3/SHF/IADD3: 64 lanes/SM/clk) while the FMA pipe (IMAD,
+// another 64 lanes/SM/clk, co-issued) idles during the hashes. ptxas chooses IADD3 for every addition it sees,
+// so the additions we want on the FMA pipe are written as a*ONE+b with ONE read from constant memory (opaque
+// to the compiler, folded into the IMAD's constant operand, no register), and x>>n as umulhi(x, 2^(32-n)).
+// Levels (compile-time, see DESIGN.md K1 "pipe balance"):
+//   ECL_SHA_FMA  0 none | 1 w+K, h+wk | 3 + e', a', S0+maj (ALU 1, FMA 5 adds per round) | 4 all 7 adds
+//   ECL_SHS_FMA  0 none | 1 w[i]+w[i+9] | 2 all three schedule adds
+//   ECL_SHR_FMA  0/1    sigma shifts x>>3, x>>10 as IMAD.HI
+//   ECL_RMD_FMA  0 none | 1 a+(w+K) | 2 + F
+#ifndef ECL_SHA_FMA
+#define ECL_SHA_FMA 3
+#endif
+#ifndef ECL_SHS_FMA
+#define ECL_SHS_FMA 2
+#endif
+#ifndef ECL_SHR_FMA
+#define ECL_SHR_FMA 1
+#endif
+#ifndef ECL_RMD_FMA
+#define ECL_RMD_FMA 1
+#endif
+static __constant__ u32 ecl_k_one = 1u;
+static __constant__ u32 ecl_k_shr3 = 1u << 29;
+static __constant__ u32 ecl_k_shr10 = 1u << 22;
+
+__device__ __forceinline__ u32 fma_add(u32 a, u32 b) {
+  u32 d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(ecl_k_one), "r"(b));
+  return d;
+}
+__device__ __forceinline__ u32 fma_mulhi(u32 a, u32 m) {
+  u32 d;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(m));
+  return d;
+}
+template <int N>
+__device__ __forceinline__ vw<N> vfadd(const vw<N> &a, const vw<N> &b) {
+  vw<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.l[i] = fma_add(a.l[i], b.l[i]);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ vw<N> vfadd(const vw<N> &a, u32 k) {
+  vw<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.l[i] = fma_add(a.l[i], k);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ vw<N> vshr3(const vw<N> &a) {
+#if ECL_SHR_FMA
+  vw<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.l[i] = fma_mulhi(a.l[i], ecl_k_shr3);
+  return r;
+#else
+  return vshr(a, 3);
+#endif
+}
+template <int N>
+__device__ __forceinline__ vw<N> vshr10(const vw<N> &a) {
+#if ECL_SHR_FMA
+  vw<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.l[i] = fma_mulhi(a.l[i], ecl_k_shr10);
+  return r;
+#else
+  return vshr(a, 10);
+#endif
+}
+
 // ---------------------------------------------------------------- SHA-256 (FIPS 180-4; lib/sha256.c:399-453)
 
 // one compression; st = chaining value in/out, w = 16 message words (big-endian loads), clobbered
@@ -95,13 +169,35 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
   for (int i = 0; i < 64; ++i) {
     if (i >= 16) {
       const vw<N> x = w[(i + 1) & 15], y = w[(i + 14) & 15];
-      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ vshr(x, 3);
-      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ vshr(y, 10);
+      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ vshr3(x);
+      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ vshr10(y);
+#if ECL_SHS_FMA == 0
       w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+#elif ECL_SHS_FMA == 1
+      w[i & 15] = vfadd(w[i & 15], w[(i + 9) & 15]) + s0 + s1;
+#else
+      w[i & 15] = vfadd(vfadd(vfadd(w[i & 15], w[(i + 9) & 15]), s0), s1);
+#endif
     }
-    const vw<N> t1 = h + (vrotr(e, 6) ^ vrotr(e, 11) ^ vrotr(e, 25)) + ((e & f) ^ (~e & g)) + (w[i & 15] + K[i]);
-    const vw<N> t2 = (vrotr(a, 2) ^ vrotr(a, 13) ^ vrotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-    h = g, g = f, f = e, e = d + t1, d = c, c = b, b = a, a = t1 + t2;
+    const vw<N> S1 = vrotr(e, 6) ^ vrotr(e, 11) ^ vrotr(e, 25), ch = (e & f) ^ (~e & g);
+    const vw<N> S0 = vrotr(a, 2) ^ vrotr(a, 13) ^ vrotr(a, 22), mj = (a & b) ^ (a & c) ^ (b & c);
+#if ECL_SHA_FMA == 0
+    const vw<N> t1 = h + S1 + ch + (w[i & 15] + K[i]);
+    const vw<N> ne = d + t1, na = t1 + (S0 + mj);
+#elif ECL_SHA_FMA == 1
+    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> t1 = p + S1 + ch;
+    const vw<N> ne = d + t1, na = t1 + S0 + mj;
+#elif ECL_SHA_FMA == 3
+    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> t1 = p + S1 + ch;
+    const vw<N> ne = vfadd(d, t1), na = vfadd(t1, vfadd(S0, mj));
+#else
+    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> t1 = vfadd(p, vfadd(S1, ch));
+    const vw<N> ne = vfadd(d, t1), na = vfadd(t1, vfadd(S0, mj));
+#endif
+    h = g, g = f, f = e, e = ne, d = c, c = b, b = a, a = na;
   }
   st[0] = st[0] + a, st[1] = st[1] + b, st[2] = st[2] + c, st[3] = st[3] + d;
   st[4] = st[4] + e, st[5] = st[5] + f, st[6] = st[6] + g, st[7] = st[7] + h;
@@ -120,9 +216,20 @@ __device__ __forceinline__ void sha256_iv(vw<N> st[8]) {
 #define RMD_F3(x, y, z) (((x) | ~(y)) ^ (z))
 #define RMD_F4(x, y, z) (((x) & (z)) | ((y) & ~(z)))
 #define RMD_F5(x, y, z) ((x) ^ ((y) | ~(z)))
+#define RMD_WK(wi, k) ((k) ? vfadd(w[wi], (u32)(k)) : w[wi])
+#if ECL_RMD_FMA == 0
 #define RMD_STEP(F, a, b, c, d, e, wi, k, s)      \
   a = vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e; \
   c = vrotl(c, 10);
+#elif ECL_RMD_FMA == 1
+#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                \
+  a = vrotl(vfadd(a, RMD_WK(wi, k)) + F(b, c, d), s) + e; \
+  c = vrotl(c, 10);
+#else
+#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                       \
+  a = vrotl(vfadd(vfadd(a, RMD_WK(wi, k)), F(b, c, d)), s) + e; \
+  c = vrotl(c, 10);
+#endif
 
 // digest words of SHA-256 (sha[0..7], big-endian word values) -> h160_t words
 template <int N>
