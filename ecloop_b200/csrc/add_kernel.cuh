@@ -44,34 +44,34 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
   BloomView bv = p.bloom;
   if (p.bloom_smem_words) bv.bits = sbloom;
 
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.T) return;
+  // Every thread of the CTA runs the same number of steps so that the CTA can sit behind barriers (lockstep,
+  // see common.cuh): threads without work of their own (past T, or past the last group) run along on the last
+  // owner's centre and only their reporting is masked.
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 T = p.T;
+  const bool owner = tid < T;
+  const u32 t = owner ? tid : T - 1;
 
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
 
   const u64 g0 = (u64)t * p.groups_per_thread;
-  u64 g1 = g0 + p.groups_per_thread;
-  if (g1 > p.n_groups) g1 = p.n_groups;
-  uint4 *scr = p.scratch + t;
-#ifdef ECL_LOCKSTEP
-  // every thread of this CTA walks the same number of groups: the warps may re-align at a barrier once per
-  // pass-2 step so that they fetch the (large, fully unrolled) hash code together
-  const bool lockstep = (u64)(blockIdx.x + 1) * blockDim.x * p.groups_per_thread <= p.n_groups;
-#endif
+  const u64 g1 = g0 + p.groups_per_thread;
+  uint4 *scr = p.scratch + tid;  // scratch is sized for whole CTAs
+  const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride
 
 #pragma unroll 1
   for (u64 g = g0; g < g1; ++g) {
+    const bool active = owner && g < p.n_groups;
     const u64 kc = p.key_off0 + g * (2 * H) + H;  // key index of the centre
 
     // ---- pass 1: prefix products e_0, e_0 e_1, ...   e_0 = step.x - px, e_{i+1} = table[i].x - px
     fe acc = fe_sub(fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]), px);
 #pragma unroll 1
     for (int i = 0; i < H; ++i) {
-      scr[(size_t)(2 * i) * T] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
-      scr[(size_t)(2 * i + 1) * T] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+      scr[(size_t)(2 * i) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      scr[(size_t)(2 * i + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
       const fe d = fe_sub(fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]), px);
       acc = fe_mul(acc, d);
     }
@@ -80,10 +80,8 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
     // ---- pass 2: peel the inverses off from the far end; two points per step
 #pragma unroll 1
     for (int i = H - 1; i >= 0; --i) {
-#ifdef ECL_LOCKSTEP
-      if (lockstep && (i % ECL_LOCKSTEP) == 0) __syncthreads();
-#endif
-      const fe pre = fe_from_u4(scr[(size_t)(2 * i) * T], scr[(size_t)(2 * i + 1) * T]);  // e_0 ... e_i
+      if (ECL_HASH_SYNC) __syncthreads();
+      const fe pre = fe_from_u4(scr[(size_t)(2 * i) * TS], scr[(size_t)(2 * i + 1) * TS]);  // e_0 ... e_i
       const fe gx = fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]);
       const fe gy = fe_from_u4(tab[i * 4 + 2], tab[i * 4 + 3]);
       const fe inv_i = fe_mul(inv, pre);  // 1 / (gx - px)
@@ -108,7 +106,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
 #pragma unroll
       for (int l = 0; l < 8; ++l) x[1][l] = rx.v[l], y[1][l] = ry.v[l];
 
-      check_points<2, A33, A65, ENDO>(bv, p.sink, x, y, off);
+      check_points<2, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x, y, off, active);
     }
 
     // ---- next group's centre: P + 2H*s*G with inv = 1/(step.x - px)

@@ -7,11 +7,16 @@
 #include "fp.cuh"
 #include "hash160.cuh"
 
+// One CTA of 512 threads per SM: all 16 warps of the SM sit behind the same barriers (ECL_HASH_SYNC), which is
+// what lets them share instruction fetches; 128 registers per thread either way.
 #ifndef ADD_THREADS
-#define ADD_THREADS 256
+#define ADD_THREADS 512
 #endif
 #ifndef ADD_MIN_BLOCKS
-#define ADD_MIN_BLOCKS 2
+#define ADD_MIN_BLOCKS 1
+#endif
+#ifndef ECL_HASH_SYNC
+#define ECL_HASH_SYNC 1  // 0: no lockstep; 1: barrier per step and between SHA-256 and RIPEMD-160; 4: + every 16 rounds
 #endif
 #ifndef ADD_H
 #define ADD_H 1024  // half group: 2*ADD_H keys share one inversion; 2048 = the reference's GROUP_INV_SIZE
@@ -79,9 +84,11 @@ __device__ __forceinline__ fe fe_beta() {
 // ---------------------------------------------------------------- hash + probe of NW points
 // check_found_add's inner loop (main.c:291-298) and its endomorphism block (main.c:300-344) for NW points at
 // once. Emission order is restored on the host (ecl_collect sorts), so lanes may report in any order.
-template <int NW, bool A33, bool A65, bool ENDO>
+// SYNC: CTA-barrier density inside the hashes (hash160.cuh); only legal when the whole CTA calls this in lockstep.
+// `active` masks the reporting of threads that only run along to keep the CTA in lockstep.
+template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0>
 __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
-                                             const u64 (&off)[NW]) {
+                                             const u64 (&off)[NW], const bool active = true) {
   constexpr int NE = ENDO ? 6 : 1;
 #pragma unroll 1
   for (int e = 0; e < NE; ++e) {
@@ -108,20 +115,20 @@ __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink 
       u32 odd[NW];
 #pragma unroll
       for (int n = 0; n < NW; ++n) odd[n] = y[n][0];
-      hash160_33<NW>(h, x, odd);
+      hash160_33<NW, SYNC>(h, x, odd);
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (bloom_has(bv, hh)) emit_hit(sink, off[n], hh, (u32)e, 0);
+        if (bloom_has(bv, hh) && active) emit_hit(sink, off[n], hh, (u32)e, 0);
       }
     }
     if (A65) {
       vw<NW> h[5];
-      hash160_65<NW>(h, x, y);
+      hash160_65<NW, SYNC>(h, x, y);
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (bloom_has(bv, hh)) emit_hit(sink, off[n], hh, (u32)e, 1);
+        if (bloom_has(bv, hh) && active) emit_hit(sink, off[n], hh, (u32)e, 1);
       }
     }
   }

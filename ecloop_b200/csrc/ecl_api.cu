@@ -50,6 +50,8 @@ struct ecl_dev {
 
   fe *d_scalars = nullptr;
   u32 scalars_cap = 0;
+  uint4 *mul_scratch = nullptr;  // 128 B per key of a mul batch (X, Y, Z, prefix product)
+  u32 mul_scratch_cap = 0;
 
   // pending work (one submit at a time)
   int pending = 0;  // 0 none, 1 add, 2 mul
@@ -199,7 +201,7 @@ extern "C" void ecl_close(ecl_dev *dev) {
   cudaDeviceSynchronize();
   cudaFree(dev->gtab), cudaFree(dev->bases), cudaFree(dev->add_table), cudaFree(dev->bloom_bits);
   cudaFree(dev->centres), cudaFree(dev->scratch), cudaFree(dev->d_hits), cudaFree(dev->d_hit_count);
-  cudaFree(dev->d_scalars);
+  cudaFree(dev->d_scalars), cudaFree(dev->mul_scratch);
   for (auto ev : dev->ev_pool) cudaEventDestroy(ev);
   if (dev->ev_begin) cudaEventDestroy(dev->ev_begin);
   if (dev->ev_end) cudaEventDestroy(dev->ev_end);
@@ -403,10 +405,23 @@ static int launch_mul(ecl_dev *dev, u32 begin, u32 end) {
   mp.scalars = dev->d_scalars + begin, mp.gtab = dev->gtab, mp.bloom = bloom_view(dev);
   mp.sink.hits = dev->d_hits, mp.sink.count = dev->d_hit_count, mp.sink.cap = dev->hit_cap;
   mp.count = end - begin;
+  // keys per thread: as many as it takes to keep ~768 threads per SM busy, so that small batches still spread
+  // over the whole GPU and large ones amortise the per-thread inversion
+  const u32 want_threads = (u32)dev->sm_count * 768u;
+  mp.B = std::min<u32>(64u, (mp.count + want_threads - 1) / want_threads);
+  if (mp.B == 0) mp.B = 1;
+  mp.T = (mp.count + mp.B - 1) / mp.B;
+  if (mp.count > dev->mul_scratch_cap) {
+    CK(cudaFree(dev->mul_scratch));
+    dev->mul_scratch = nullptr, dev->mul_scratch_cap = 0;
+    CK(cudaMalloc(&dev->mul_scratch, ((size_t)mp.count + 64) * 128));
+    dev->mul_scratch_cap = mp.count;
+  }
+  mp.scratch = dev->mul_scratch;
   cudaEvent_t e0 = next_event(dev), e1 = next_event(dev);
   if (!e0 || !e1) return fail(dev, ECL_E_CUDA, "cudaEventCreate failed");
   CK(cudaEventRecord(e0, dev->stream));
-  pick_mul_kernel(dev->p_flags)<<<(mp.count + 127) / 128, 128, 0, dev->stream>>>(mp);
+  pick_mul_kernel(dev->p_flags)<<<(mp.T + 127) / 128, 128, 0, dev->stream>>>(mp);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, dev->stream));
   dev->launches++;

@@ -154,10 +154,10 @@ __device__ __forceinline__ fe fe_neg(const fe &a) {
   return r;
 }
 
-// acc[0..7] += {a0,a1,a2,a3} * b, the four 64-bit products sitting side by side (an aligned "row");
-// returns the carry out of acc[7]. Each {mad.lo.cc, madc.hi.cc} pair becomes one IMAD.WIDE.U32(.X).
-__device__ __forceinline__ u32 fp_mad_row(u32 *acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
-  u32 c;
+// acc[0..7] += {a0,a1,a2,a3} * b, the four 64-bit products sitting side by side (an aligned "row"); the carry
+// out of acc[7] is added into acc[8]. Each {mad.lo.cc, madc.hi.cc} pair becomes one IMAD.WIDE.U32(.X) and the
+// trailing addc one IADD3.X, so a row is 4 FMA-pipe + 1 ALU-pipe instructions.
+__device__ __forceinline__ void fp_mad_row_c(u32 *acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
   asm("mad.lo.cc.u32  %0, %9, %13, %0;\n\t"
       "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
       "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
@@ -166,15 +166,42 @@ __device__ __forceinline__ u32 fp_mad_row(u32 *acc, u32 a0, u32 a1, u32 a2, u32 
       "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
       "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
       "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-      "addc.u32       %8, 0, 0;"
+      "addc.u32       %8, %8, 0;"
       : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
-        "+r"(acc[7]), "=r"(c)
+        "+r"(acc[7]), "+r"(acc[8])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// same, for a row whose top limb is the top of the whole product (no carry can leave it)
+__device__ __forceinline__ void fp_mad_row_top(u32 *acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
+  asm("mad.lo.cc.u32  %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32    %7, %11, %12, %7;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// returns the carry instead of adding it somewhere (used by the reduction)
+__device__ __forceinline__ u32 fp_mad_row(u32 *acc, u32 a0, u32 a1, u32 a2, u32 a3, u32 b) {
+  u32 c = 0;
+  u32 tmp[9];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tmp[k] = acc[k];
+  tmp[8] = 0;
+  fp_mad_row_c(tmp, a0, a1, a2, a3, b);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = tmp[k];
+  c = tmp[8];
   return c;
 }
 
 // t[0..15] = a * b  (schoolbook, 64 IMAD.WIDE). Position k of the even accumulator e is limb k; position k of
-// the odd accumulator o is limb k+1.
+// the odd accumulator o is limb k+1. Rows are issued in order of b[i]; a row's carry lands in the limb just
+// above it, which only ever holds such carries until the next row of the same parity covers it.
 __device__ __forceinline__ void fp_mul_wide(u32 t[16], const fe &a, const fe &b) {
   u32 e[16], o[16];
 #pragma unroll
@@ -183,13 +210,13 @@ __device__ __forceinline__ void fp_mul_wide(u32 t[16], const fe &a, const fe &b)
   for (int i = 0; i < 8; ++i) {
     {  // products a[j]*b[i] with i+j even -> limbs i+j, i+j+1 of e
       const int j0 = i & 1, s = i + j0;
-      const u32 c = fp_mad_row(e + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
-      if (s + 8 < 16) e[s + 8] += c;  // e[s+8] <= 1 before this ("carry bookkeeping")
+      if (s + 8 < 16) fp_mad_row_c(e + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
+      else fp_mad_row_top(e + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
     }
     {  // products with i+j odd -> limbs i+j, i+j+1 = o[i+j-1], o[i+j]
       const int j0 = (i + 1) & 1, s = i + j0 - 1;
-      const u32 c = fp_mad_row(o + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
-      if (s + 8 < 16) o[s + 8] += c;
+      if (s + 8 < 16) fp_mad_row_c(o + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
+      else fp_mad_row_top(o + s, a.v[j0], a.v[j0 + 2], a.v[j0 + 4], a.v[j0 + 6], b.v[i]);
     }
   }
   // t = e + (o << 32)

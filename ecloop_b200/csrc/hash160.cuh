@@ -153,7 +153,17 @@ __device__ __forceinline__ vw<N> vshr10(const vw<N> &a) {
 // ---------------------------------------------------------------- SHA-256 (FIPS 180-4; lib/sha256.c:399-453)
 
 // one compression; st = chaining value in/out, w = 16 message words (big-endian loads), clobbered
-template <int N>
+// SYNC != 0: the caller guarantees that every thread of the CTA runs this function the same number of times, and
+// the warps re-align at a CTA barrier every 16 rounds / 32 steps so that they share instruction fetches (the
+// unrolled hashes are ~100 KB of code, far beyond the instruction caches; see DESIGN.md K1 "lockstep")
+template <int SYNC>
+__device__ __forceinline__ void hash_sync_point() {
+  if (SYNC) __syncthreads();
+}
+
+// CMASK: bit i set = message word i is a compile-time constant (padding); additions with such words stay plain C
+// so that the compiler folds them, everything else is steered by the ECL_*_FMA levels above.
+template <int N, int SYNC = 0, u32 CMASK = 0>
 __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
   constexpr u32 K[64] = {
       0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
@@ -165,18 +175,35 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
       0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
       0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
   vw<N> a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+  bool wc[64];  // wc[i]: schedule word i is a compile-time constant (evaluated by the compiler after unrolling)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) wc[i] = (CMASK >> i) & 1u;
+#pragma unroll
+  for (int i = 16; i < 64; ++i) wc[i] = wc[i - 16] && wc[i - 15] && wc[i - 7] && wc[i - 2];
 #pragma unroll
   for (int i = 0; i < 64; ++i) {
+    if (SYNC > 1 && i > 0 && (i % (64 / SYNC)) == 0) hash_sync_point<SYNC>();
     if (i >= 16) {
       const vw<N> x = w[(i + 1) & 15], y = w[(i + 14) & 15];
-      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ vshr3(x);
-      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ vshr10(y);
+      const bool cA = wc[i - 16], cB = wc[i - 15], cC = wc[i - 7], cD = wc[i - 2];
+      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ (cB ? vshr(x, 3) : vshr3(x));
+      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ (cD ? vshr(y, 10) : vshr10(y));
 #if ECL_SHS_FMA == 0
       w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
-#elif ECL_SHS_FMA == 1
-      w[i & 15] = vfadd(w[i & 15], w[(i + 9) & 15]) + s0 + s1;
 #else
-      w[i & 15] = vfadd(vfadd(vfadd(w[i & 15], w[(i + 9) & 15]), s0), s1);
+      // constant terms are summed in plain C (folded), the others on the FMA pipe
+      vw<N> kc = vset<N>(0), r = vset<N>(0);
+      bool have = false;
+      const vw<N> term[4] = {w[i & 15], w[(i + 9) & 15], s0, s1};
+      const bool tc[4] = {cA, cC, cB, cD};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (tc[q]) kc = kc + term[q];
+        else if (!have) r = term[q], have = true;
+        else if (ECL_SHS_FMA == 1 && q >= 2) r = r + term[q];
+        else r = vfadd(r, term[q]);
+      }
+      w[i & 15] = have ? r + kc : kc;
 #endif
     }
     const vw<N> S1 = vrotr(e, 6) ^ vrotr(e, 11) ^ vrotr(e, 25), ch = (e & f) ^ (~e & g);
@@ -185,15 +212,15 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
     const vw<N> t1 = h + S1 + ch + (w[i & 15] + K[i]);
     const vw<N> ne = d + t1, na = t1 + (S0 + mj);
 #elif ECL_SHA_FMA == 1
-    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> p = vfadd(h, wc[i] ? w[i & 15] + K[i] : vfadd(w[i & 15], K[i]));
     const vw<N> t1 = p + S1 + ch;
     const vw<N> ne = d + t1, na = t1 + S0 + mj;
 #elif ECL_SHA_FMA == 3
-    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> p = vfadd(h, wc[i] ? w[i & 15] + K[i] : vfadd(w[i & 15], K[i]));
     const vw<N> t1 = p + S1 + ch;
     const vw<N> ne = vfadd(d, t1), na = vfadd(t1, vfadd(S0, mj));
 #else
-    const vw<N> p = vfadd(h, vfadd(w[i & 15], K[i]));
+    const vw<N> p = vfadd(h, wc[i] ? w[i & 15] + K[i] : vfadd(w[i & 15], K[i]));
     const vw<N> t1 = vfadd(p, vfadd(S1, ch));
     const vw<N> ne = vfadd(d, t1), na = vfadd(t1, vfadd(S0, mj));
 #endif
@@ -217,22 +244,26 @@ __device__ __forceinline__ void sha256_iv(vw<N> st[8]) {
 #define RMD_F4(x, y, z) (((x) & (z)) | ((y) & ~(z)))
 #define RMD_F5(x, y, z) ((x) ^ ((y) | ~(z)))
 #define RMD_WK(wi, k) ((k) ? vfadd(w[wi], (u32)(k)) : w[wi])
+// message words 8..15 are padding constants: a + F + (w + K) is then one IADD3 with an immediate
+#define RMD_CONSTW(wi) ((wi) >= 8)
 #if ECL_RMD_FMA == 0
 #define RMD_STEP(F, a, b, c, d, e, wi, k, s)      \
   a = vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e; \
   c = vrotl(c, 10);
 #elif ECL_RMD_FMA == 1
-#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                \
-  a = vrotl(vfadd(a, RMD_WK(wi, k)) + F(b, c, d), s) + e; \
+#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                                           \
+  a = RMD_CONSTW(wi) ? vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e                    \
+                     : vrotl(vfadd(a, RMD_WK(wi, k)) + F(b, c, d), s) + e;             \
   c = vrotl(c, 10);
 #else
-#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                       \
-  a = vrotl(vfadd(vfadd(a, RMD_WK(wi, k)), F(b, c, d)), s) + e; \
+#define RMD_STEP(F, a, b, c, d, e, wi, k, s)                                           \
+  a = RMD_CONSTW(wi) ? vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e                    \
+                     : vrotl(vfadd(vfadd(a, RMD_WK(wi, k)), F(b, c, d)), s) + e;       \
   c = vrotl(c, 10);
 #endif
 
 // digest words of SHA-256 (sha[0..7], big-endian word values) -> h160_t words
-template <int N>
+template <int N, int SYNC = 0>
 __device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) {
   vw<N> w[16];
 #pragma unroll
@@ -244,7 +275,10 @@ __device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) 
   const u32 h0 = 0x67452301u, h1 = 0xefcdab89u, h2 = 0x98badcfeu, h3 = 0x10325476u, h4 = 0xc3d2e1f0u;
   vw<N> al = vset<N>(h0), bl = vset<N>(h1), cl = vset<N>(h2), dl = vset<N>(h3), el = vset<N>(h4);
   vw<N> ar = al, br = bl, cr = cl, dr = dl, er = el;
+#define RMD_ROUND_BOUNDARY \
+  if (SYNC > 1) hash_sync_point<SYNC>();
 #include "rmd160_steps.inc"
+#undef RMD_ROUND_BOUNDARY
   out[0] = vbswap(cl + dr + h1);
   out[1] = vbswap(dl + er + h2);
   out[2] = vbswap(el + ar + h3);
@@ -256,7 +290,7 @@ __device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) 
 
 // X[i] = big-endian word i of the coordinate = limb 7-i (little-endian 32-bit limbs)
 // compressed key 02|03 || X (lib/addr.c:33-45): one block
-template <int N>
+template <int N, int SYNC = 0>
 __device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y_odd)[N]) {
   vw<N> w[16], st[8];
 #pragma unroll
@@ -270,12 +304,13 @@ __device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], c
   for (int i = 9; i < 15; ++i) w[i] = vset<N>(0);
   w[15] = vset<N>(33 * 8);
   sha256_iv(st);
-  sha256_compress(st, w);
-  rmd160_of_sha(out, st);
+  sha256_compress<N, SYNC, 0xFE00u>(st, w);
+  hash_sync_point<SYNC>();
+  rmd160_of_sha<N, SYNC>(out, st);
 }
 
 // uncompressed key 04 || X || Y (lib/addr.c:47-67): two blocks
-template <int N>
+template <int N, int SYNC = 0>
 __device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y)[N][8]) {
   vw<N> w[16], st[8];
 #pragma unroll
@@ -288,12 +323,14 @@ __device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], c
     for (int i = 9; i < 16; ++i) w[i].l[n] = __funnelshift_r(y[n][15 - i], y[n][16 - i], 8);
   }
   sha256_iv(st);
-  sha256_compress(st, w);
+  sha256_compress<N, SYNC>(st, w);
+  hash_sync_point<SYNC>();
 #pragma unroll
   for (int n = 0; n < N; ++n) w[0].l[n] = (y[n][0] << 24) | 0x00800000u;
 #pragma unroll
   for (int i = 1; i < 15; ++i) w[i] = vset<N>(0);
   w[15] = vset<N>(65 * 8);
-  sha256_compress(st, w);
-  rmd160_of_sha(out, st);
+  sha256_compress<N, SYNC, 0xFFFEu>(st, w);
+  hash_sync_point<SYNC>();
+  rmd160_of_sha<N, SYNC>(out, st);
 }

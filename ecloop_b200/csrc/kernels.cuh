@@ -48,24 +48,60 @@ __global__ void __launch_bounds__(128) smul_kernel(const SmulParams p) {
 struct MulParams {
   const fe *scalars;
   const uint4 *gtab;
+  uint4 *scratch;  // per key 8 x 16 B (X, Y, Z, prefix product), slot-major: [(m*8 + q)*T + t]
   BloomView bloom;
   HitSink sink;
-  u32 count;
+  u32 count;  // keys
+  u32 T;      // threads that own keys
+  u32 B;      // keys per thread: thread t owns keys m*T + t, m < B (coalesced scalar loads)
 };
 
+__device__ __forceinline__ void st_fe(uint4 *p, size_t stride, const fe &a) {
+  p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  p[stride] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_from_u4(p[0], p[stride]); }
+
+// ec_gtable_mul x n + ec_jacobi_grprdc + check_found_mul (main.c:531-534). The reference normalises a job of
+// 2048 projective points with ONE inversion (lib/ecc.c:695-707); here every thread does the same over its own B
+// keys: pass 1 computes k*G in Jacobian coordinates and the running product of the Z's (X, Y, Z and the prefix
+// go to a coalesced scratch), one Fermat inversion per thread, pass 2 peels 1/Z off from the far end, converts
+// to affine, hashes and probes. A key = 0 (mod n) has no point: it rides along as Z = 1 and is skipped.
 template <bool A33, bool A65>
 __global__ void __launch_bounds__(128) mul_kernel(const MulParams p) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= p.count) return;
-  const fe k = p.scalars[j];
-  jac a;
-  if (!gtab_mul(a, k, p.gtab)) return;  // k = 0 (mod n): no public key
-  fe fx, fy;
-  jac_to_affine(fx, fy, a);
-  u32 x[1][8], y[1][8];
-  for (int l = 0; l < 8; ++l) x[0][l] = fx.v[l], y[0][l] = fy.v[l];
-  const u64 off[1] = {j};
-  check_points<1, A33, A65, false>(p.bloom, p.sink, x, y, off);
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.T) return;
+  const size_t T = p.T;
+  uint4 *scr = p.scratch + t;
+  fe acc = fe_one();
+#pragma unroll 1
+  for (u32 m = 0; m < p.B; ++m) {
+    const u32 j = m * p.T + t;
+    jac a;
+    bool ok = false;
+    if (j < p.count) ok = gtab_mul(a, p.scalars[j], p.gtab);
+    if (!ok) a.x = fe_zero(), a.y = fe_zero(), a.z = fe_one();
+    uint4 *slot = scr + (size_t)m * 8 * T;
+    st_fe(slot, T, a.x), st_fe(slot + 2 * T, T, a.y), st_fe(slot + 4 * T, T, a.z), st_fe(slot + 6 * T, T, acc);
+    acc = fe_mul_noinline(acc, a.z);
+  }
+  fe inv = fe_inv(acc);
+#pragma unroll 1
+  for (int m = (int)p.B - 1; m >= 0; --m) {
+    const uint4 *slot = scr + (size_t)m * 8 * T;
+    const fe z = ld_fe(slot + 4 * T, T), pre = ld_fe(slot + 6 * T, T);
+    const fe zi = fe_mul_noinline(inv, pre);
+    inv = fe_mul_noinline(inv, z);
+    const fe ax = ld_fe(slot, T), ay = ld_fe(slot + 2 * T, T);
+    if (fe_is_zero(ax) && fe_is_zero(ay)) continue;  // no point for this slot
+    const fe zi2 = fe_mul_noinline(zi, zi);
+    const fe fx = fe_mul_noinline(ax, zi2), fy = fe_mul_noinline(ay, fe_mul_noinline(zi2, zi));
+    u32 x[1][8], y[1][8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) x[0][l] = fx.v[l], y[0][l] = fy.v[l];
+    const u64 off[1] = {(u64)m * p.T + t};
+    check_points<1, A33, A65, false>(p.bloom, p.sink, x, y, off);
+  }
 }
 
 // ---------------------------------------------------------------- window table build (one-off per device)

@@ -30,12 +30,12 @@
 
 #include "../../include/ecloop_b200.h"
 #include "filter.h"
+#include "mulfeed.h"
 #include "sha256_host.h"
 #include "u256.h"
 
 #define ECLOOP_VERSION "0.5.0"           /* the reference version this CLI mirrors (main.c:15) */
 #define JOB_KEYS_MAX (2u * 1024 * 1024) /* MAX_JOB_SIZE (main.c:16) */
-#define LINE_MAX_CHARS 1025             /* MAX_LINE_SIZE (main.c:18) */
 #define MUL_BATCH_KEYS (1u << 20)       /* keys per ecl_mul_submit */
 
 enum command { CMD_NONE, CMD_ADD, CMD_MUL, CMD_RND };
@@ -71,11 +71,7 @@ typedef struct app {
   bool finished;
   int fatal; /* a rank thread hit a library error */
 
-  /* mul: batches handed from the stdin reader to the rank threads */
-  pthread_cond_t q_nonempty, q_nonfull;
-  struct mul_batch *q_head, *q_tail;
-  int q_len, q_cap;
-  bool q_closed;
+  struct mul_pipe *mul; /* mul: stdin reader -> parser threads -> rank threads */
 } app;
 
 static uint64_t now_ms(void) {
@@ -441,105 +437,160 @@ static void cmd_rnd(app *a) {
 
 /* ------------------------------------------------------------------ mul (main.c:458-578) */
 
-typedef struct mul_batch {
-  struct mul_batch *next;
-  uint32_t count;
-  uint64_t keys[MUL_BATCH_KEYS][4];
-} mul_batch;
+/* The reference reads stdin with fgets on one thread and parses on the workers (main.c:549-569, 503-527). At GPU
+ * speed the text side is the bottleneck (10 M keys = 650 MB of hex), so the feeder is a three-stage pipeline:
+ *   reader (main thread)   fread()s large blocks, cuts them at a line boundary, numbers them;
+ *   parser threads (-t)    split a block into lines with the reference's rules and turn each into a key;
+ *   rank threads (per GPU) take parsed blocks IN SEQUENCE ORDER, fuse them into submits of up to 2^20 keys.
+ * With one GPU the found lines therefore come out in input order, like `-t 1`. */
 
-static void queue_push(app *a, mul_batch *b) {
-  pthread_mutex_lock(&a->mu);
-  while (a->q_len >= a->q_cap && !a->fatal) pthread_cond_wait(&a->q_nonfull, &a->mu);
-  b->next = NULL;
-  if (a->q_tail) a->q_tail->next = b;
-  else a->q_head = b;
-  a->q_tail = b;
-  a->q_len++;
-  pthread_cond_signal(&a->q_nonempty);
-  pthread_mutex_unlock(&a->mu);
-}
+#define MUL_BLOCK_BYTES (8u << 20)
+#define MUL_RING 16 /* blocks in flight */
 
-static mul_batch *queue_pop(app *a) {
-  pthread_mutex_lock(&a->mu);
-  while (!a->q_head && !a->q_closed) pthread_cond_wait(&a->q_nonempty, &a->mu);
-  mul_batch *b = a->q_head;
-  if (b) {
-    a->q_head = b->next;
-    if (!a->q_head) a->q_tail = NULL;
-    a->q_len--;
-    pthread_cond_signal(&a->q_nonfull);
+typedef struct mul_block {
+  char *text;          /* raw bytes, whole lines (the last block may lack the final newline) */
+  size_t len;
+  uint64_t (*keys)[4]; /* parsed keys */
+  uint32_t count, cap;
+  int state;           /* 0 free, 1 text ready, 2 being parsed, 3 parsed */
+  uint64_t seq;
+} mul_block;
+
+typedef struct mul_pipe {
+  app *a;
+  mul_block ring[MUL_RING];
+  uint64_t seq_read, seq_parse, seq_take; /* next sequence number to fill / to parse / to hand to a GPU */
+  uint32_t take_off;                      /* keys of block seq_take already handed out */
+  bool eof;
+  pthread_cond_t cv;
+} mul_pipe;
+
+static void *mul_parser_main(void *p) {
+  mul_pipe *mp = p;
+  app *a = mp->a;
+  for (;;) {
+    pthread_mutex_lock(&a->mu);
+    while (!(mp->seq_parse < mp->seq_read) && !mp->eof && !a->fatal) pthread_cond_wait(&mp->cv, &a->mu);
+    if (!(mp->seq_parse < mp->seq_read) || a->fatal) {
+      pthread_mutex_unlock(&a->mu);
+      return NULL;
+    }
+    mul_block *b = &mp->ring[mp->seq_parse++ % MUL_RING];
+    b->state = 2;
+    pthread_mutex_unlock(&a->mu);
+    b->count = mulfeed_parse(b->text, b->len, a->raw_text, &b->keys, &b->cap);
+    pthread_mutex_lock(&a->mu);
+    b->state = 3;
+    pthread_cond_broadcast(&mp->cv);
+    pthread_mutex_unlock(&a->mu);
   }
-  pthread_mutex_unlock(&a->mu);
-  return b;
 }
 
 static void *mul_rank_main(void *p) {
-  app *a = ((rank_arg *)p)->a;
+  mul_pipe *mp = ((rank_arg *)p)->a->mul;
+  app *a = mp->a;
   ecl_dev *dev = a->dev[((rank_arg *)p)->rank];
   hit_buf hb = {0};
-  mul_batch *b;
-  while ((b = queue_pop(a)) != NULL) {
+  uint64_t(*keys)[4] = malloc((size_t)MUL_BATCH_KEYS * sizeof *keys);
+  if (!keys) die("out of memory");
+  for (;;) {
+    /* take parsed blocks in sequence order until the submit is full */
     uint32_t n = 0;
-    if (ecl_mul_submit(dev, (const uint64_t(*)[4])b->keys, b->count, a->flags & (ECL_A33 | ECL_A65)) != ECL_OK) {
+    pthread_mutex_lock(&a->mu);
+    for (;;) {
+      mul_block *b = &mp->ring[mp->seq_take % MUL_RING];
+      const bool ready = mp->seq_take < mp->seq_read && b->state == 3;
+      if (ready) { /* a block of very short lines can hold more keys than one submit: take it in parts */
+        const uint32_t avail = b->count - mp->take_off, room = MUL_BATCH_KEYS - n, k = avail < room ? avail : room;
+        memcpy(keys + n, b->keys + mp->take_off, (size_t)k * sizeof *keys);
+        n += k, mp->take_off += k;
+        if (mp->take_off == b->count) {
+          b->state = 0, mp->take_off = 0;
+          mp->seq_take++;
+          pthread_cond_broadcast(&mp->cv);
+        }
+        if (n == MUL_BATCH_KEYS) break;
+        continue;
+      }
+      if (n || a->fatal) break;                           /* something to do (or giving up) */
+      if (mp->eof && mp->seq_take == mp->seq_read) break; /* drained */
+      pthread_cond_wait(&mp->cv, &a->mu);
+    }
+    pthread_mutex_unlock(&a->mu);
+    if (!n || a->fatal) break;
+    uint32_t nh = 0;
+    if (ecl_mul_submit(dev, (const uint64_t(*)[4])keys, n, a->flags & (ECL_A33 | ECL_A65)) != ECL_OK) {
       fprintf(stderr, "ecloop: GPU error: %s\n", ecl_last_error(dev));
       a->fatal = 1;
-    } else if (collect_hits(a, dev, &hb, &n) == 0) {
-      for (uint32_t i = 0; i < n; ++i) /* check_found_mul (main.c:458-479): no verification on this path */
-        if (filter_exact(&a->filter, hb.hits[i].h160))
-          write_found(a, hb.hits[i].kind, hb.hits[i].h160, b->keys[hb.hits[i].key_off]);
-      progress_add(a, b->count);
+    } else if (collect_hits(a, dev, &hb, &nh) == 0) {
+      for (uint32_t i = 0; i < nh; ++i) /* check_found_mul (main.c:458-479): no verification on this path */
+        if (filter_exact(&a->filter, hb.hits[i].h160)) write_found(a, hb.hits[i].kind, hb.hits[i].h160, keys[hb.hits[i].key_off]);
+      progress_add(a, n);
     }
-    free(b);
     if (a->fatal) {
       pthread_mutex_lock(&a->mu);
-      pthread_cond_broadcast(&a->q_nonfull);
+      pthread_cond_broadcast(&mp->cv);
       pthread_mutex_unlock(&a->mu);
       break;
     }
   }
+  free(keys);
   free(hb.hits), free(hb.pks), free(hb.xy), free(hb.h33), free(hb.h65);
   return NULL;
 }
 
-static void line_to_key(const app *a, uint64_t key[4], const char *line, size_t len) {
-  if (!a->raw_text) {
-    modn_from_hex(key, line); /* main.c:504 */
-    return;
-  }
-  uint32_t d[8]; /* -raw: key = SHA-256(line), big-endian, not reduced (main.c:506-527) */
-  sha256_bytes(d, (const uint8_t *)line, len);
-  for (int i = 0; i < 4; ++i) key[i] = (uint64_t)d[6 - 2 * i] << 32 | d[7 - 2 * i];
-}
-
 static void cmd_mul(app *a) {
-  pthread_t th[64];
+  static mul_pipe pipe;
+  mul_pipe *mp = &pipe;
+  mp->a = a, a->mul = mp;
+  pthread_cond_init(&mp->cv, NULL);
+  pthread_t rank_th[64], parse_th[64];
   rank_arg arg[64];
-  a->q_cap = 2 * a->n_gpus + 1;
+  int n_parsers = (int)(a->threads_shown < 16 ? a->threads_shown : 16);
+  for (int i = 0; i < n_parsers; ++i) pthread_create(&parse_th[i], NULL, mul_parser_main, mp);
   for (int r = 0; r < a->n_gpus; ++r) {
     arg[r].a = a, arg[r].rank = r;
-    pthread_create(&th[r], NULL, mul_rank_main, &arg[r]);
+    pthread_create(&rank_th[r], NULL, mul_rank_main, &arg[r]);
   }
-  char line[LINE_MAX_CHARS];
-  mul_batch *b = NULL;
-  while (!a->fatal && fgets(line, sizeof line, stdin)) { /* same line protocol as main.c:552-556 */
-    size_t len = strlen(line);
-    if (len && line[len - 1] == '\n') line[--len] = 0;
-    if (len && line[len - 1] == '\r') line[--len] = 0;
-    if (!len) continue;
-    if (!b) {
-      b = malloc(sizeof *b);
-      if (!b) die("out of memory");
-      b->count = 0;
+
+  /* reader: blocks of whole lines; the tail after the last newline moves to the front of the next block */
+  char *carry = malloc(MUL_BLOCK_BYTES + 2);
+  size_t carry_len = 0;
+  if (!carry) die("out of memory");
+  for (bool more = true; more && !a->fatal;) {
+    pthread_mutex_lock(&a->mu);
+    while (mp->seq_read - mp->seq_take >= MUL_RING && !a->fatal) pthread_cond_wait(&mp->cv, &a->mu);
+    mul_block *b = &mp->ring[mp->seq_read % MUL_RING];
+    pthread_mutex_unlock(&a->mu);
+    if (a->fatal) break;
+    if (!b->text && !(b->text = malloc(MUL_BLOCK_BYTES + 2))) die("out of memory");
+    memcpy(b->text, carry, carry_len);
+    size_t have = carry_len;
+    carry_len = 0;
+    const size_t got = fread(b->text + have, 1, MUL_BLOCK_BYTES - have, stdin);
+    have += got;
+    if (have < MUL_BLOCK_BYTES) more = false; /* EOF (or error): this is the last block */
+    size_t cut = have;
+    if (more) { /* keep whole lines; a block without any newline is passed on as is (pieces of 1024 characters) */
+      cut = mulfeed_cut(b->text, have);
+      carry_len = have - cut;
+      memcpy(carry, b->text + cut, carry_len);
     }
-    line_to_key(a, b->keys[b->count++], line, len);
-    if (b->count == MUL_BATCH_KEYS) queue_push(a, b), b = NULL;
+    b->len = cut;
+    pthread_mutex_lock(&a->mu);
+    b->seq = mp->seq_read, b->state = 1;
+    mp->seq_read++;
+    if (!more) mp->eof = true;
+    pthread_cond_broadcast(&mp->cv);
+    pthread_mutex_unlock(&a->mu);
   }
-  if (b) queue_push(a, b);
   pthread_mutex_lock(&a->mu);
-  a->q_closed = true;
-  pthread_cond_broadcast(&a->q_nonempty);
+  mp->eof = true;
+  pthread_cond_broadcast(&mp->cv);
   pthread_mutex_unlock(&a->mu);
-  for (int r = 0; r < a->n_gpus; ++r) pthread_join(th[r], NULL);
+  for (int i = 0; i < n_parsers; ++i) pthread_join(parse_th[i], NULL);
+  for (int r = 0; r < a->n_gpus; ++r) pthread_join(rank_th[r], NULL);
+  free(carry);
   if (a->fatal) exit(1);
   finish(a);
 }
@@ -664,8 +715,6 @@ static void setup(app *a) { /* init (main.c:774-865) */
   if (opt_flag(a, "-endo") && a->cmd != CMD_MUL) a->flags |= ECL_ENDO;
 
   pthread_mutex_init(&a->mu, NULL);
-  pthread_cond_init(&a->q_nonempty, NULL);
-  pthread_cond_init(&a->q_nonfull, NULL);
   long cpus = sysconf(_SC_NPROCESSORS_ONLN);
   if (cpus < 1) cpus = 1;
   const char *t = opt_value(a, "-t");

@@ -174,3 +174,75 @@ def test_cli_without_gpu_fails_loudly(hl):
     r = subprocess.run([str(HOST / "ecloop"), "add", "-f", str(GOLD / "btc-puzzles-hash"), "-r", "8000:ffff"],
                        capture_output=True, text=True, stdin=subprocess.DEVNULL)
     assert r.returncode == 1 and "no CPU compute path" in r.stderr and r.stdout == ""
+
+
+# ---------------------------------------------------------------- mul feeder (stdin text -> keys)
+
+
+def fgets_pieces(data: bytes, maxlen: int = 1024):
+    """what `fgets(line, 1025, stdin)` + the two strips + the empty-line skip of main.c:552-556 yield"""
+    out, pos = [], 0
+    while pos < len(data):
+        nl = data.find(b"\n", pos, pos + maxlen)
+        take = nl - pos + 1 if nl != -1 else min(maxlen, len(data) - pos)
+        piece = data[pos:pos + take]
+        pos += take
+        if piece.endswith(b"\n"):
+            piece = piece[:-1]
+        if piece.endswith(b"\r"):
+            piece = piece[:-1]
+        if piece:
+            out.append(piece)
+    return out
+
+
+def run_mulfeed(hl, data: bytes, raw: bool):
+    hl.mulfeed_parse.restype = C.c_uint32
+    hl.mulfeed_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_bool, C.POINTER(C.POINTER(C.c_uint64 * 4)), C.POINTER(C.c_uint32)]
+    buf = C.create_string_buffer(data, len(data) + 2)
+    keys = C.POINTER(C.c_uint64 * 4)()
+    cap = C.c_uint32(0)
+    n = hl.mulfeed_parse(buf, len(data), raw, C.byref(keys), C.byref(cap))
+    assert buf.raw[:len(data)] == data  # the text is left untouched
+    return [I(keys[i]) for i in range(n)]
+
+
+def test_mulfeed_matches_reference_line_rules(hl):
+    import ecloop_b200.host as H
+
+    rng = random.Random(3)
+    lines = [b"%064x" % rng.getrandbits(256) for _ in range(50)]
+    lines += [b"1", b"", b"c936", b"0xdeadbeef", b"  12 34  ", b"\r", b"abc\r", b"f" * 64, b"zz", b"%x" % (N + 7),
+              b"a" * 1024, b"b" * 1025, b"7" * 3000, b"hello world", b"9\r\r"]
+    for sep in (b"\n", b"\r\n"):
+        data = sep.join(lines) + sep + b"tail-without-newline"
+        want_hex = [H.fe_modn_from_hex(p.decode()) for p in fgets_pieces(data)]
+        assert run_mulfeed(hl, data, False) == want_hex
+        want_raw = [H.raw_to_key(p) for p in fgets_pieces(data)]
+        assert run_mulfeed(hl, data, True) == want_raw
+    # the golden stdin files of the reference dumps
+    for name, raw in (("mul_keys_24.txt", False), ("mul_raw_8.txt", True)):
+        data = (GOLD / name).read_bytes()
+        want = [H.raw_to_key(p) if raw else H.fe_modn_from_hex(p.decode()) for p in fgets_pieces(data)]
+        assert run_mulfeed(hl, data, raw) == want
+
+
+def test_mulfeed_cut_keeps_whole_lines(hl):
+    hl.mulfeed_cut.restype = C.c_size_t
+    hl.mulfeed_cut.argtypes = [C.c_char_p, C.c_size_t]
+    assert hl.mulfeed_cut(b"ab\ncd\nef", 8) == 6
+    assert hl.mulfeed_cut(b"ab\n", 3) == 3
+    assert hl.mulfeed_cut(b"x" * 2500, 2500) == 2048  # no newline: whole 1024-character pieces
+    assert hl.mulfeed_cut(b"x" * 100, 100) == 0
+    # cutting + parsing block by block gives the same keys as parsing the whole text
+    rng = random.Random(9)
+    data = b"".join(b"%x\n" % rng.getrandbits(rng.randrange(1, 256)) for _ in range(400))
+    whole = run_mulfeed(hl, data, False)
+    got, carry, block = [], b"", 997
+    for off in range(0, len(data), block):
+        chunk = carry + data[off:off + block]
+        last = off + block >= len(data)
+        cut = len(chunk) if last else hl.mulfeed_cut(chunk, len(chunk))
+        got += run_mulfeed(hl, chunk[:cut], False)
+        carry = chunk[cut:]
+    assert got == whole
