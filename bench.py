@@ -126,6 +126,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def measured_traffic():
+    """DRAM bytes per key of add_kernel from the committed `ncu --set full` capture (tools/summarize_ncu.py)"""
+    p = ROOT / "profiles" / "add_kernel_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["dram_bytes_per_key"]), d.get("source", str(p))
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -285,6 +295,8 @@ def ours_arm(args):
         achieved_tops = hot_rate * ALU_OPS_PER_KEY / 1e12
         hbm_achieved = hot_rate * SCRATCH_BYTES_PER_KEY * 2 / 1e9
         clocks = sampler.summary()
+        per_launch_keys = args.steps * step_keys / max(1, launches // (2 * world))  # launches counts smul + add pairs
+        traffic_per_key, traffic_src = measured_traffic()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mkeys/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
@@ -302,7 +314,10 @@ def ours_arm(args):
             "gpu_launches": launches,
             "roofline": {
                 "bound": "int_alu", "achieved": round(achieved_tops, 3), "peak": round(alu_peak_tops, 3), "unit": "Tops/s",
-                "frac": round(achieved_tops / alu_peak_tops, 4), "traffic": None,
+                "frac": round(achieved_tops / alu_peak_tops, 4),
+                "traffic": round(traffic_per_key * per_launch_keys) if traffic_per_key else None,
+                "traffic_note": (f"bytes per add_kernel launch of {int(per_launch_keys)} keys = {traffic_per_key:.2f} B/key DRAM read+write "
+                                 f"measured by ncu ({traffic_src}); algorithmic bytes: {SCRATCH_BYTES_PER_KEY} B/key") if traffic_per_key else None,
                 "model": f"{ALU_OPS_PER_KEY} canonical ALU-pipe int32 ops per key (SURVEY 8d) x add_kernel keys/s (CUDA events around its launches)",
                 "peak_source": "measured in this process: LOP3.LUT issue rate over all SMs (ecl_peak_bench)",
                 "pipes": {k: round(v, 1) for k, v in peaks.items()},

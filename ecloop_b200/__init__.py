@@ -23,7 +23,10 @@ ABI_SYMBOLS = (
     "ecl_abi_version", "ecl_device_count", "ecl_open", "ecl_close", "ecl_last_error", "ecl_set_stream",
     "ecl_set_filter", "ecl_set_stride", "ecl_add_submit", "ecl_mul_submit", "ecl_collect", "ecl_last_elapsed_ms",
     "ecl_set_tuning", "ecl_prim_fp", "ecl_prim_scalar_mul", "ecl_prim_hash160", "ecl_prim_bloom", "ecl_peak_bench",
+    "ecl_peak_bench_kind",
 )
+PEAK_KINDS = ("lop3", "iadd3", "shf", "imad", "imad_wide", "lop3+imad", "imad_const", "imad_hi", "lop3+imad_const",
+              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf")
 
 
 class EclError(RuntimeError):
@@ -82,6 +85,7 @@ def load_library(rebuild: bool = False) -> C.CDLL:
     lib.ecl_prim_hash160.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.ecl_prim_bloom.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.ecl_peak_bench.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.ecl_peak_bench_kind.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -237,6 +241,16 @@ class Device:
         d = {k + "_gops": float(out[i]) for i, k in enumerate(keys)}
         d["sm_mhz"] = float(out[6])
         return d
+
+
+    def peak_bench_kinds(self):
+        """every instruction kind / mix of csrc/peak.cuh -> {name: Gops/s}"""
+        out = {}
+        for k, name in enumerate(PEAK_KINDS):
+            g, mhz = C.c_double(0), C.c_double(0)
+            self._ck(self._lib.ecl_peak_bench_kind(self._h, k, C.byref(g), C.byref(mhz)))
+            out[name] = round(float(g.value), 1)
+        return out
 
 
 def device_count() -> int:

@@ -5,6 +5,11 @@
 
 #include "add_kernel.cuh"
 
+// the compressed-only, no-endomorphism variant (the headline path) runs the software-pipelined kernel
+#ifndef ECL_ADD_SP
+#define ECL_ADD_SP 1
+#endif
+
 #ifndef ADD_VARIANT
 #error "compile with -DADD_VARIANT=<flags 1..3 or 5..7>"
 #endif
@@ -15,7 +20,11 @@
 #define CAT(a, b) CAT2(a, b)
 
 cudaError_t CAT(ecl_add_launch_, ADD_VARIANT)(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
+#if ECL_ADD_SP && ADD_VARIANT == 1
+  auto fn = add_kernel_sp<ADD_H>;
+#else
   auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO>;
+#endif
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   fn<<<grid, ADD_THREADS, smem, stream>>>(p);

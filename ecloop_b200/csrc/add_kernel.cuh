@@ -120,3 +120,172 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
   }
 }
 
+
+// ---------------------------------------------------------------- K1-sp: software-pipelined addr33 variant
+// Same work as add_kernel<H, true, false, false>, restructured so that every basic block of the hot loop holds
+// one hash160 (ALU-pipe: LOP3/SHF/IADD3) AND the field arithmetic that produces the next point (FMA-pipe:
+// IMAD.WIDE): ptxas interleaves the two independent streams, so the two integer pipes work at the same time
+// instead of taking turns (in add_kernel the whole CTA alternates between an FMA-bound field phase and an
+// ALU-bound hash phase). One pass-2 step = block X: hash(P - (i+1)G) || form P + (i+1)G, then block Y:
+// hash(P + (i+1)G) || peel the inverse of step i-1 and form P - iG.
+
+// hash160 of one compressed point, probe, report; used where nothing is pipelined (once per group)
+static __device__ __noinline__ void check_one_slow(const BloomView &bv, const HitSink &sink, const fe &x, u32 y0, u64 off,
+                                                   bool active) {
+  u32 xx[1][8], odd[1] = {y0};
+#pragma unroll
+  for (int l = 0; l < 8; ++l) xx[0][l] = x.v[l];
+  vw<1> h[5];
+  hash160_33<1, 0>(h, xx, odd);
+  const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
+  if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, 0, 0);
+}
+
+// Pass 1 of the NEXT group (its prefix products) rides in block X as well, so after the first group of a launch
+// there is no field-only phase left: the group step is the element peeled FIRST (it is multiplied in last), which
+// makes the next centre known at the start of pass 2, and the prefixes go to the other half of a ping-pong scratch.
+// Elements of a group: f_i = table[i].x - px (i < H), f_H = step.x - px; scratch entry k holds q_k = f_0 ... f_{k-1}.
+template <int H>
+__global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(const AddParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) u64 mbar;
+  uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
+  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw + (H + 1) * 64);
+  const u32 tab_bytes = (H + 1) * 64;
+  const u32 bloom_bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;
+
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&mbar, tab_bytes + bloom_bytes);
+    bulk_g2s(tab, p.table, tab_bytes, &mbar);
+    if (bloom_bytes) bulk_g2s(sbloom, p.bloom.bits, bloom_bytes, &mbar);
+  }
+  mbar_wait(&mbar, 0);
+
+  BloomView bv = p.bloom;
+  if (p.bloom_smem_words) bv.bits = sbloom;
+
+  const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 T = p.T;
+  const bool owner = tid < T;
+  const u32 t = owner ? tid : T - 1;
+
+  fe px, py;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
+
+  const u64 g0 = (u64)t * p.groups_per_thread;
+  const u64 g1 = g0 + p.groups_per_thread;
+  const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride (scratch is sized for whole CTAs)
+  uint4 *scr_cur = p.scratch + tid;                  // entry k, half h at [(2k + h) * TS]
+  uint4 *scr_nxt = scr_cur + (size_t)2 * (H + 1) * TS;
+  const fe sx = fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]);
+
+  // ---- pass 1 of this thread's first group (the only one that is not hidden behind hashing)
+  fe tot;
+  {
+    fe acc = fe_one();
+#pragma unroll 1
+    for (int k = 0; k < H; ++k) {
+      scr_cur[(size_t)(2 * k) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      scr_cur[(size_t)(2 * k + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+      acc = fe_mul(acc, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), px));
+    }
+    scr_cur[(size_t)(2 * H) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    scr_cur[(size_t)(2 * H + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+    tot = fe_mul(acc, fe_sub(sx, px));
+  }
+
+#pragma unroll 1
+  for (u64 g = g0; g < g1; ++g) {
+    const bool active = owner && g < p.n_groups;
+    const u64 kc = p.key_off0 + g * (2 * H) + H;
+
+    fe inv = fe_inv(tot);  // 1 / (f_0 ... f_H)
+
+    // ---- the group step first: next centre N = P + 2H*s*G
+    fe nx, ny;
+    {
+      const fe qH = fe_from_u4(scr_cur[(size_t)(2 * H) * TS], scr_cur[(size_t)(2 * H + 1) * TS]);
+      const fe inv_s = fe_mul(inv, qH);  // 1 / f_H
+      inv = fe_mul(inv, fe_sub(sx, px));  // 1 / q_H
+      const fe sy = fe_from_u4(tab[H * 4 + 2], tab[H * 4 + 3]);
+      affine_add_inv(nx, ny, px, py, sx, sy, inv_s);
+    }
+
+    // the centre itself (key K) takes the slot of the far end K+H, which lies outside the group
+    check_one_slow(bv, p.sink, px, py.v[0], kc, active);
+
+    // ---- prologue: operands and inverse of step H-1, and its first point P - H*G
+    fe gx = fe_from_u4(tab[(H - 1) * 4 + 0], tab[(H - 1) * 4 + 1]);
+    fe gy = fe_from_u4(tab[(H - 1) * 4 + 2], tab[(H - 1) * 4 + 3]);
+    fe inv_i;
+    {
+      const fe q = fe_from_u4(scr_cur[(size_t)(2 * (H - 1)) * TS], scr_cur[(size_t)(2 * (H - 1) + 1) * TS]);
+      inv_i = fe_mul(inv, q);
+      inv = fe_mul(inv, fe_sub(gx, px));
+    }
+    fe ax, ay;  // the point waiting to be hashed
+    affine_add_inv(ax, ay, px, py, gx, fe_neg(gy), inv_i);
+    fe accn = fe_one();  // q'_k of the next group
+
+    // ---- pass 2, pipelined
+#pragma unroll 1
+    for (int i = H - 1; i >= 1; --i) {
+      if (ECL_HASH_SYNC) __syncthreads();
+      // block X: hash P - (i+1)G  ||  form P + (i+1)G, and one pass-1 step of the next group
+      u32 xx[1][8], odd[1];
+      vw<1> h[5];
+#pragma unroll
+      for (int l = 0; l < 8; ++l) xx[0][l] = ax.v[l];
+      odd[0] = ay.v[0];
+      hash160_33<1, 0>(h, xx, odd);
+      fe bx, by;
+      affine_add_inv(bx, by, px, py, gx, gy, inv_i);
+      {
+        const int k = H - 1 - i;
+        scr_nxt[(size_t)(2 * k) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+        scr_nxt[(size_t)(2 * k + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+        accn = fe_mul(accn, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), nx));
+      }
+      {
+        const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
+        if (bloom_has(bv, hh) && active) emit_hit(p.sink, kc - (u64)(i + 1), hh, 0, 0);
+      }
+      // block Y: hash P + (i+1)G  ||  peel step i-1 and form P - iG
+#pragma unroll
+      for (int l = 0; l < 8; ++l) xx[0][l] = bx.v[l];
+      odd[0] = by.v[0];
+      hash160_33<1, 0>(h, xx, odd);
+      {
+        const fe q = fe_from_u4(scr_cur[(size_t)(2 * (i - 1)) * TS], scr_cur[(size_t)(2 * (i - 1) + 1) * TS]);
+        gx = fe_from_u4(tab[(i - 1) * 4 + 0], tab[(i - 1) * 4 + 1]);
+        gy = fe_from_u4(tab[(i - 1) * 4 + 2], tab[(i - 1) * 4 + 3]);
+        inv_i = fe_mul(inv, q);
+        inv = fe_mul(inv, fe_sub(gx, px));
+        affine_add_inv(ax, ay, px, py, gx, fe_neg(gy), inv_i);
+      }
+      {
+        const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
+        if (bloom_has(bv, hh) && active && i != H - 1) emit_hit(p.sink, kc + (u64)(i + 1), hh, 0, 0);
+      }
+    }
+    // ---- epilogue: step 0 (keys K-1 and K+1), the last two prefixes of the next group
+    {
+      fe bx, by;
+      affine_add_inv(bx, by, px, py, gx, gy, inv_i);
+      check_one_slow(bv, p.sink, ax, ay.v[0], kc - 1, active);
+      check_one_slow(bv, p.sink, bx, by.v[0], kc + 1, active);
+      scr_nxt[(size_t)(2 * (H - 1)) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+      scr_nxt[(size_t)(2 * (H - 1) + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+      accn = fe_mul(accn, fe_sub(fe_from_u4(tab[(H - 1) * 4 + 0], tab[(H - 1) * 4 + 1]), nx));
+      scr_nxt[(size_t)(2 * H) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+      scr_nxt[(size_t)(2 * H + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+      tot = fe_mul(accn, fe_sub(sx, nx));
+    }
+    px = nx, py = ny;
+    uint4 *sw = scr_cur;
+    scr_cur = scr_nxt, scr_nxt = sw;
+  }
+}

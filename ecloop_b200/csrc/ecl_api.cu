@@ -268,7 +268,9 @@ static BloomView bloom_view(const ecl_dev *dev) {
 
 static int ensure_add_resources(ecl_dev *dev) {
   if (!dev->centres) CK(cudaMalloc(&dev->centres, (size_t)dev->Tmax * 16 * sizeof(u32)));
-  if (!dev->scratch) CK(cudaMalloc(&dev->scratch, (size_t)dev->Tmax * ADD_H * 32));
+  // prefix products: (ADD_H + 1) entries of 32 B per thread, twice (the pipelined kernel ping-pongs between the
+  // current group's prefixes and the next group's)
+  if (!dev->scratch) CK(cudaMalloc(&dev->scratch, (size_t)dev->Tmax * (ADD_H + 1) * 32 * 2));
   if (!dev->table_valid) {  // ctx_precompute_gpoints (main.c:219-246) on the device
     SmulParams sp;
     memset(&sp, 0, sizeof sp);
@@ -649,6 +651,35 @@ static int run_peak(ecl_dev *dev, double *gops, double *mhz) {
   // waves; with 8 blocks/SM all resident it is one wave, so cycles/time ~ SM clock
   *mhz = (double)cycles / (best * 1e-3) / 1e6;
   return ECL_OK;
+}
+
+// one kind of peak.cuh by number (0..15); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
+extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz) {
+  if (!dev || !gops) return ECL_E_ARG;
+  CK(cudaSetDevice(dev->ordinal));
+  double mhz = 0;
+  int rc;
+  switch (kind) {
+  case 0: rc = run_peak<0>(dev, gops, &mhz); break;
+  case 1: rc = run_peak<1>(dev, gops, &mhz); break;
+  case 2: rc = run_peak<2>(dev, gops, &mhz); break;
+  case 3: rc = run_peak<3>(dev, gops, &mhz); break;
+  case 4: rc = run_peak<4>(dev, gops, &mhz); break;
+  case 5: rc = run_peak<5>(dev, gops, &mhz); break;
+  case 6: rc = run_peak<6>(dev, gops, &mhz); break;
+  case 7: rc = run_peak<7>(dev, gops, &mhz); break;
+  case 8: rc = run_peak<8>(dev, gops, &mhz); break;
+  case 9: rc = run_peak<9>(dev, gops, &mhz); break;
+  case 10: rc = run_peak<10>(dev, gops, &mhz); break;
+  case 11: rc = run_peak<11>(dev, gops, &mhz); break;
+  case 12: rc = run_peak<12>(dev, gops, &mhz); break;
+  case 13: rc = run_peak<13>(dev, gops, &mhz); break;
+  case 14: rc = run_peak<14>(dev, gops, &mhz); break;
+  case 15: rc = run_peak<15>(dev, gops, &mhz); break;
+  default: return fail(dev, ECL_E_ARG, "unknown peak kind %d", kind);
+  }
+  if (sm_mhz) *sm_mhz = mhz;
+  return rc;
 }
 
 extern "C" int ecl_peak_bench(ecl_dev *dev, double out[8]) {

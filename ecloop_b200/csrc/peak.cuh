@@ -11,6 +11,8 @@
 #define PEAK_CHAINS 8
 #define PEAK_UNROLL 4
 
+static __constant__ uint32_t peak_k_one = 1u;  // same trick as hash160.cuh: an opaque multiplicand in constant memory
+
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
   uint32_t r[PEAK_CHAINS];
@@ -35,6 +37,38 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed,
           if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
           else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(m), "r"(z));
         }
+        // ---- the instruction forms the hashes steer onto the FMA pipe (hash160.cuh)
+        if (KIND == 6) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(peak_k_one), "r"(z));  // IMAD, constant-bank operand
+        if (KIND == 7) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[c]) : "r"(m));                      // IMAD.HI
+        if (KIND == 8) {  // LOP3 + IMAD(const) co-issue
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(peak_k_one), "r"(z));
+        }
+        if (KIND == 9) {  // SHF + IMAD.WIDE co-issue
+          if (c & 1) asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(r[c]));
+          else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(q[c]) : "r"(r[c]), "r"(m));
+        }
+        if (KIND == 10) {  // LOP3 + IMAD.HI co-issue
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(r[c]) : "r"(m));
+        }
+        if (KIND == 11) {  // the hash kernels' ratio: 5 ALU-pipe : 3 FMA-pipe
+          if (c < 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(peak_k_one), "r"(z));
+        }
+        if (KIND == 13) {  // LOP3 + IMAD.WIDE: does the 64-bit multiply-add take an ALU-pipe slot as well?
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(q[c]) : "r"(r[c]), "r"(m));
+        }
+        if (KIND == 14) {  // SHF + IMAD
+          if (c & 1) asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(r[c]));
+          else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(m), "r"(z));
+        }
+        if (KIND == 15) {  // LOP3 + SHF (both ALU pipe: no gain expected)
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(r[c]));
+        }
+        if (KIND == 12) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[c]) : "r"(z));  // 2-input add: IADD3 or IMAD.IADD, ptxas decides
       }
     }
   }

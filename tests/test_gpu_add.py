@@ -191,6 +191,21 @@ def test_many_threads_ragged_tail(dev, H, E):
         dev.set_tuning(0, 0)
 
 
+def test_large_bloom_in_hbm(dev, H, E):
+    """a filter too large for shared memory (8 MB, like a `.blf` file) is probed in HBM: same hits, same false
+    positives as the oracle's blf_has"""
+    size = (1 << 20) + 3  # words, not a power of two: exercises the 64-bit modulo by a runtime size
+    flt = sparse_filter(H, 17, size, 0.88)
+    dev.set_filter(flt.bits)
+    oflt = O.HostFilter(flt.bits.ctypes.data_as(C.POINTER(C.c_uint64)), size, None)
+    for flags, oflags in ((E.A33 | E.ENDO, O.A33 | O.ENDO), (E.A33 | E.A65, O.A33 | O.A65)):
+        start = 2**70 + 99999
+        got = dev.batch_add(start, 4096, flags)
+        n, want = O.add_span(start, 1, 4096, oflags, oflt)
+        assert n > 100
+        assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
+
+
 # ---------------------------------------------------------------- size-independent properties at full size
 
 
