@@ -88,16 +88,16 @@ __device__ __forceinline__ vw<N> vset(u32 c) {
 //   ECL_SHR_FMA  0/1    sigma shifts x>>3, x>>10 as IMAD.HI
 //   ECL_RMD_FMA  0 none | 1 a+(w+K) | 2 + F
 #ifndef ECL_SHA_FMA
-#define ECL_SHA_FMA 3
+#define ECL_SHA_FMA 4
 #endif
 #ifndef ECL_SHS_FMA
-#define ECL_SHS_FMA 1
+#define ECL_SHS_FMA 2
 #endif
 #ifndef ECL_SHR_FMA
 #define ECL_SHR_FMA 0  // IMAD.HI runs at half rate and blocks the ALU pipe too (peak.cuh kinds 7, 10): keep SHF
 #endif
 #ifndef ECL_RMD_FMA
-#define ECL_RMD_FMA 1
+#define ECL_RMD_FMA 2
 #endif
 static __constant__ u32 ecl_k_one = 1u;
 static __constant__ u32 ecl_k_shr3 = 1u << 29;
