@@ -141,6 +141,10 @@ static __device__ __noinline__ void check_one_slow(const BloomView &bv, const Hi
   if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, 0, 0);
 }
 
+// Pass 1 of the NEXT group (its prefix products) rides in block X as well, so after the first group of a launch
+// there is no field-only phase left: the group step is the element peeled FIRST (it is multiplied in last), which
+// makes the next centre known at the start of pass 2, and the prefixes go to the other half of a ping-pong scratch.
+// Elements of a group: f_i = table[i].x - px (i < H), f_H = step.x - px; scratch entry k holds q_k = f_0 ... f_{k-1}.
 template <int H>
 __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(const AddParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

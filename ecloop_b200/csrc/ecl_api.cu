@@ -268,7 +268,9 @@ static BloomView bloom_view(const ecl_dev *dev) {
 
 static int ensure_add_resources(ecl_dev *dev) {
   if (!dev->centres) CK(cudaMalloc(&dev->centres, (size_t)dev->Tmax * 16 * sizeof(u32)));
-  if (!dev->scratch) CK(cudaMalloc(&dev->scratch, (size_t)dev->Tmax * ADD_H * 32));
+  // prefix products: (ADD_H + 1) entries of 32 B per thread, twice (add_kernel_sp ping-pongs between the current
+  // group's prefixes and the next group's)
+  if (!dev->scratch) CK(cudaMalloc(&dev->scratch, (size_t)dev->Tmax * (ADD_H + 1) * 32 * 2));
   if (!dev->table_valid) {  // ctx_precompute_gpoints (main.c:219-246) on the device
     SmulParams sp;
     memset(&sp, 0, sizeof sp);
