@@ -29,6 +29,7 @@
 #include <unistd.h>
 
 #include "../../include/ecloop_b200.h"
+#include "blftool.h"
 #include "filter.h"
 #include "mulfeed.h"
 #include "sha256_host.h"
@@ -73,6 +74,12 @@ typedef struct app {
 
   struct mul_pipe *mul; /* mul: stdin reader -> parser threads -> rank threads */
 } app;
+
+static uint64_t now_us(void) {
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return (uint64_t)tv.tv_sec * 1000000 + (uint64_t)tv.tv_usec;
+}
 
 static uint64_t now_ms(void) {
   struct timeval tv;
@@ -463,6 +470,7 @@ typedef struct mul_pipe {
   uint32_t take_off;                      /* keys of block seq_take already handed out */
   bool eof;
   pthread_cond_t cv;
+  uint64_t us_read, us_parse, us_gpu, us_report; /* stage totals for ECLOOP_VERBOSE */
 } mul_pipe;
 
 static void *mul_parser_main(void *p) {
@@ -478,8 +486,11 @@ static void *mul_parser_main(void *p) {
     mul_block *b = &mp->ring[mp->seq_parse++ % MUL_RING];
     b->state = 2;
     pthread_mutex_unlock(&a->mu);
+    const uint64_t t0 = now_us();
     b->count = mulfeed_parse(b->text, b->len, a->raw_text, &b->keys, &b->cap);
+    const uint64_t dt = now_us() - t0;
     pthread_mutex_lock(&a->mu);
+    mp->us_parse += dt;
     b->state = 3;
     pthread_cond_broadcast(&mp->cv);
     pthread_mutex_unlock(&a->mu);
@@ -519,13 +530,18 @@ static void *mul_rank_main(void *p) {
     pthread_mutex_unlock(&a->mu);
     if (!n || a->fatal) break;
     uint32_t nh = 0;
+    const uint64_t t0 = now_us();
     if (ecl_mul_submit(dev, (const uint64_t(*)[4])keys, n, a->flags & (ECL_A33 | ECL_A65)) != ECL_OK) {
       fprintf(stderr, "ecloop: GPU error: %s\n", ecl_last_error(dev));
       a->fatal = 1;
     } else if (collect_hits(a, dev, &hb, &nh) == 0) {
+      const uint64_t t1 = now_us();
       for (uint32_t i = 0; i < nh; ++i) /* check_found_mul (main.c:458-479): no verification on this path */
         if (filter_exact(&a->filter, hb.hits[i].h160)) write_found(a, hb.hits[i].kind, hb.hits[i].h160, keys[hb.hits[i].key_off]);
       progress_add(a, n);
+      pthread_mutex_lock(&a->mu);
+      mp->us_gpu += t1 - t0, mp->us_report += now_us() - t1;
+      pthread_mutex_unlock(&a->mu);
     }
     if (a->fatal) {
       pthread_mutex_lock(&a->mu);
@@ -567,7 +583,9 @@ static void cmd_mul(app *a) {
     memcpy(b->text, carry, carry_len);
     size_t have = carry_len;
     carry_len = 0;
+    const uint64_t tr = now_us();
     const size_t got = fread(b->text + have, 1, MUL_BLOCK_BYTES - have, stdin);
+    mp->us_read += now_us() - tr;
     have += got;
     if (have < MUL_BLOCK_BYTES) more = false; /* EOF (or error): this is the last block */
     size_t cut = have;
@@ -592,6 +610,9 @@ static void cmd_mul(app *a) {
   for (int r = 0; r < a->n_gpus; ++r) pthread_join(rank_th[r], NULL);
   free(carry);
   if (a->fatal) exit(1);
+  if (getenv("ECLOOP_VERBOSE"))
+    fprintf(stderr, "\nmul stages: read %.3f s, parse %.3f s (sum over %d threads), gpu submit+collect %.3f s, report %.3f s\n",
+            mp->us_read / 1e6, mp->us_parse / 1e6, n_parsers, mp->us_gpu / 1e6, mp->us_report / 1e6);
   finish(a);
 }
 
@@ -637,7 +658,7 @@ static void parse_offs_size(app *a) { /* load_offs_size, SURVEY A.2 */
   a->ord_size = size;
 }
 
-static void usage(const char *name) { /* main.c:750-772; the blf-gen/bench tools of the reference are not part of this build */
+static void usage(const char *name) { /* main.c:750-772; the reference's self-benchmark commands are not part of this build */
   printf("Usage: %s <cmd> [-t <threads>] [-f <file>] [-a <addr_type>] [-r <range>]\n", name);
   printf("v%s ~ https://github.com/vladkens/ecloop\n", ECLOOP_VERSION);
   printf("\nCompute commands:\n");
@@ -653,6 +674,9 @@ static void usage(const char *name) { /* main.c:750-772; the blf-gen/bench tools
   printf("  -d <offs:size>  - bit offset and size for search (example: 128:32, default: 0:32)\n");
   printf("  -q              - quiet mode (no output to stdout; -o required)\n");
   printf("  -endo           - use endomorphism (default: false)\n");
+  printf("\nOther commands:\n");
+  printf("  blf-gen         - create bloom filter from list of hex-encoded hash160\n");
+  printf("  blf-check       - check bloom filter for given hex-encoded hash160\n");
   printf("\nB200 build:\n");
   printf("  -gpus <n>       - number of GPUs to use (default: all visible; env ECLOOP_GPUS)\n");
   printf("\n");
@@ -684,6 +708,10 @@ static void open_devices(app *a) {
 }
 
 static void setup(app *a) { /* init (main.c:774-865) */
+  if (a->argc > 1) { /* the offline bloom tools come first, like main.c:776-778; they need no GPU */
+    if (!strcmp(a->argv[1], "blf-gen")) exit(blf_gen_main(a->argc, a->argv));
+    if (!strcmp(a->argv[1], "blf-check")) exit(blf_check_main(a->argc, a->argv));
+  }
   a->color = isatty(fileno(stdout));
   a->cmd = CMD_NONE;
   if (a->argc > 1) {

@@ -47,7 +47,7 @@ int bloom_save(const char *path, const uint64_t *bits, uint64_t size_words) {
   return ok ? 0 : -1;
 }
 
-static int bloom_load(ecl_filter *f, const char *path) {
+int filter_load_blf(ecl_filter *f, const char *path) {
   FILE *fp = fopen(path, "rb");
   if (!fp) {
     fprintf(stderr, "failed to open input file\n");
@@ -113,7 +113,7 @@ int filter_load(ecl_filter *f, const char *path) {
   const char *ext = strrchr(path, '.');
   if (ext && strcmp(ext, ".blf") == 0) {
     fclose(fp);
-    return bloom_load(f, path);
+    return filter_load_blf(f, path);
   }
 
   /* Text list. The reference reads with fgets into a 41-byte buffer and keeps only reads of exactly 40

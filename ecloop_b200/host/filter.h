@@ -24,6 +24,7 @@ typedef struct ecl_filter {
 
 /* returns 0, or -1 after printing the reference's message for the failure to stderr */
 int filter_load(ecl_filter *f, const char *path);
+int filter_load_blf(ecl_filter *f, const char *path); /* a `.blf` file whatever its name (blf_load, lib/utils.c:362) */
 void filter_free(ecl_filter *f);
 /* second stage of ctx_check_hash: exact membership in list mode, always true in bloom-only mode */
 bool filter_exact(const ecl_filter *f, const uint32_t h[5]);

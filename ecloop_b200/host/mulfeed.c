@@ -10,10 +10,7 @@
 
 static void line_to_key(uint64_t key[4], char *line, size_t len, bool raw) {
   if (!raw) { /* main.c:504 */
-    const char saved = line[len];
-    line[len] = 0;
-    modn_from_hex(key, line);
-    line[len] = saved;
+    modn_from_hex_n(key, line, len);
     return;
   }
   uint32_t d[8]; /* -raw: key = SHA-256(line) read as a big-endian 256-bit number, not reduced (main.c:506-527) */

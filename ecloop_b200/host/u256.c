@@ -1,7 +1,6 @@
 /* u256.c — see u256.h. Host bookkeeping only: nothing here touches a curve point or a hash. */
 #include "u256.h"
 
-#include <ctype.h>
 #include <string.h>
 
 typedef unsigned __int128 u128;
@@ -104,22 +103,32 @@ void modn_add_stride(u256 r, const u256 base, const u256 stride, uint64_t off) {
   modn_add(r, t, base);
 }
 
-void u256_from_hex(u256 r, const char *hex) {
+/* nibble value of a character, 0xFF for anything that is not a hex digit */
+static uint8_t HEXVAL[256];
+static void hexval_init(void) __attribute__((constructor));
+static void hexval_init(void) {
+  memset(HEXVAL, 0xFF, sizeof HEXVAL);
+  for (int c = '0'; c <= '9'; ++c) HEXVAL[c] = (uint8_t)(c - '0');
+  for (int c = 'a'; c <= 'f'; ++c) HEXVAL[c] = (uint8_t)(c - 'a' + 10);
+  for (int c = 'A'; c <= 'F'; ++c) HEXVAL[c] = (uint8_t)(c - 'A' + 10);
+}
+
+void u256_from_hex_n(u256 r, const char *hex, size_t len) {
   u256_set64(r, 0);
-  size_t len = strlen(hex);
   unsigned cnt = 0;
   while (len-- > 0) {
-    const int ch = tolower((unsigned char)hex[len]);
-    uint64_t v;
-    if (ch >= '0' && ch <= '9') v = (uint64_t)(ch - '0');
-    else if (ch >= 'a' && ch <= 'f') v = (uint64_t)(ch - 'a' + 10);
-    else continue;
-    if (cnt < 64) r[cnt / 16] |= v << (4 * (cnt % 16)); /* the reference writes past the array here */
+    const uint8_t v = HEXVAL[(unsigned char)hex[len]];
+    if (v == 0xFF) continue;
+    if (cnt < 64) r[cnt / 16] |= (uint64_t)v << (4 * (cnt % 16)); /* the reference writes past the array here */
     cnt++;
   }
 }
 
-void modn_from_hex(u256 r, const char *hex) {
-  u256_from_hex(r, hex);
+void u256_from_hex(u256 r, const char *hex) { u256_from_hex_n(r, hex, strlen(hex)); }
+
+void modn_from_hex_n(u256 r, const char *hex, size_t len) {
+  u256_from_hex_n(r, hex, len);
   if (u256_cmp(r, SECP_N) >= 0) modn_sub(r, r, SECP_N);
 }
+
+void modn_from_hex(u256 r, const char *hex) { modn_from_hex_n(r, hex, strlen(hex)); }

@@ -36,5 +36,7 @@ void modn_add_stride(u256 r, const u256 base, const u256 stride, uint64_t off); 
 
 /* right-to-left hex parse that skips non-hex characters (lib/ecc.c:81-95); digits beyond 64 are dropped */
 void u256_from_hex(u256 r, const char *hex);
+void u256_from_hex_n(u256 r, const char *hex, size_t len); /* same, explicit length (no terminator needed) */
 void modn_from_hex(u256 r, const char *hex); /* + one conditional subtraction of n (lib/ecc.c:262-265) */
+void modn_from_hex_n(u256 r, const char *hex, size_t len);
 #endif

@@ -246,3 +246,60 @@ def test_mulfeed_cut_keeps_whole_lines(hl):
         got += run_mulfeed(hl, chunk[:cut], False)
         carry = chunk[cut:]
     assert got == whole
+
+
+# ---------------------------------------------------------------- blf-gen / blf-check (host tools, no GPU)
+
+
+def _run(exe, args, stdin=b"", cwd=None):
+    r = subprocess.run([str(exe), *args], input=stdin, capture_output=True, timeout=120, cwd=cwd)
+    return r.returncode, r.stdout.decode(), r.stderr.decode()
+
+
+def test_blf_gen_and_check_match_reference(hl, tmp_path):
+    """`make blf` (Makefile:35-44): create, update, size mismatch, check — same bytes, same text as the reference"""
+    ref_bin = O.REF_DIR / "ecloop_ref"
+    if not ref_bin.exists():
+        pytest.skip("oracle/_ref not built")
+    ours = HOST / "ecloop"
+    puzzles = (GOLD / "btc-puzzles-hash").read_bytes()
+    bw = (GOLD / "btc-bw-hash").read_bytes()
+    outs = {}
+    for name, exe in (("ours", ours), ("ref", ref_bin)):
+        d = tmp_path / name
+        d.mkdir()
+        log = []
+        log.append(_run(exe, ["blf-gen", "-n", "32768", "-o", "t.blf"], puzzles, cwd=d))          # creating: added 160
+        log.append(_run(exe, ["blf-gen", "-n", "32768", "-o", "t.blf"], bw, cwd=d))               # updating: added 1081 (A.7)
+        log.append(_run(exe, ["blf-gen", "-n", "32768", "-o", "t.blf"], puzzles, cwd=d))          # nothing new
+        log.append(_run(exe, ["blf-gen", "-n", "1000", "-o", "t.blf"], puzzles, cwd=d))           # size mismatch
+        log.append(_run(exe, ["blf-gen", "-o", "t.blf"], b"", cwd=d))                             # missing -n
+        log.append(_run(exe, ["blf-gen", "-n", "5"], b"", cwd=d))                                 # missing -o
+        log.append(_run(exe, ["blf-check", "-f", "t.blf", "751e76e8199196d454941c45d1b3a323f1433bd6", "0" * 40, "short"], cwd=d))
+        log.append(_run(exe, ["blf-check", "-f", "t.blf"], b"  7025b4efb3ff42eb4d6d71fab6b53b4f4967e3dd \nnope\n" + b"f" * 40 + b"\n", cwd=d))
+        log.append(_run(exe, ["blf-check"], cwd=d))
+        log.append(_run(exe, ["blf-check", "-f", "missing.blf", "0" * 40], cwd=d))
+        norm = [(rc, out.replace(str(exe), "ecloop"), err) for rc, out, err in log]
+        outs[name] = (norm, (d / "t.blf").read_bytes())
+    assert outs["ours"][1] == outs["ref"][1]
+    assert outs["ours"][1][:16] == struct.pack("<IIQ", 0x45434246, 1, 22084)  # SURVEY 8c: n=32768 -> 22 084 words
+    for a, b in zip(outs["ours"][0], outs["ref"][0]):
+        assert a == b
+    assert "added 160 new items" in outs["ours"][0][0][1] and "added 1,081 new items" in outs["ours"][0][1][1].replace("1081", "1,081")
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 123457, 50_000_000])
+def test_blf_gen_sizing_matches_reference(hl, tmp_path, n):
+    ref_bin = O.REF_DIR / "ecloop_ref"
+    if not ref_bin.exists():
+        pytest.skip("oracle/_ref not built")
+    if n > 10_000_000:  # only compare the printed parameters (the file would be 270 MB): feed nothing, kill nothing
+        a = _run(HOST / "ecloop", ["blf-gen", "-n", str(n), "-o", str(tmp_path / "a.blf")])
+        b = _run(ref_bin, ["blf-gen", "-n", str(n), "-o", str(tmp_path / "b.blf")])
+        assert a[1].splitlines()[1] == b[1].splitlines()[1]
+        assert (tmp_path / "a.blf").stat().st_size == (tmp_path / "b.blf").stat().st_size
+        return
+    h = b"".join(hashlib.sha1(b"%d" % i).hexdigest().encode() + b"\n" for i in range(min(n, 500)))
+    _run(HOST / "ecloop", ["blf-gen", "-n", str(n), "-o", str(tmp_path / "a.blf")], h)
+    _run(ref_bin, ["blf-gen", "-n", str(n), "-o", str(tmp_path / "b.blf")], h)
+    assert (tmp_path / "a.blf").read_bytes() == (tmp_path / "b.blf").read_bytes()

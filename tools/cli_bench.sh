@@ -31,7 +31,7 @@ print("planted", len(picked))
 PY
 ls -la /tmp/mul_keys.txt
 echo "== ours: mul -a cu, all $N keys"
-( time timeout 600 $BIN mul -f /tmp/mul_filter.txt -a cu -q -o /tmp/mul_ours.txt -gpus 1 < /tmp/mul_keys.txt ) 2>&1 | tr '\r' '\n' | grep -E "Mkeys|real" | tail -2
+( export ECLOOP_VERBOSE=1; time timeout 600 $BIN mul -f /tmp/mul_filter.txt -a cu -q -o /tmp/mul_ours.txt -gpus 1 < /tmp/mul_keys.txt ) 2>&1 | tr '\r' '\n' | grep -E "Mkeys|real|stages" | tail -3
 echo "== ours: mul -a cu -t 1 (one parser thread)"
 ( time timeout 600 $BIN mul -f /tmp/mul_filter.txt -a cu -q -o /tmp/mul_ours1.txt -gpus 1 -t 1 < /tmp/mul_keys.txt ) 2>&1 | tr '\r' '\n' | grep -E "Mkeys|real" | tail -2
 echo "== reference: mul -a cu, first 1000000 keys, -t $(nproc)"
