@@ -31,12 +31,12 @@
 #include "../../include/ecloop_b200.h"
 #include "blftool.h"
 #include "filter.h"
+#include "jobplan.h"
 #include "mulfeed.h"
 #include "sha256_host.h"
 #include "u256.h"
 
 #define ECLOOP_VERSION "0.5.0"           /* the reference version this CLI mirrors (main.c:15) */
-#define JOB_KEYS_MAX (2u * 1024 * 1024) /* MAX_JOB_SIZE (main.c:16) */
 #define MUL_BATCH_KEYS (1u << 20)       /* keys per ecl_mul_submit */
 
 enum command { CMD_NONE, CMD_ADD, CMD_MUL, CMD_RND };
@@ -60,12 +60,10 @@ typedef struct app {
   /* search range (add, rnd) */
   u256 range_s, range_e, stride;
   unsigned ord_offs, ord_size;
-  uint64_t job_keys;  /* ctx->job_size */
-  uint64_t span_jobs; /* jobs fused per submit */
 
   /* job dispenser + progress, all under `mu` */
   pthread_mutex_t mu;
-  u256 next, first, job_inc;
+  job_plan plan;
   uint64_t k_checked, k_found;
   uint64_t t_start, t_update, t_print, t_pause_at, paused_ms;
   volatile bool paused;
@@ -259,24 +257,10 @@ static int report_add_hits(app *a, ecl_dev *dev, hit_buf *hb, uint32_t n, const 
 
 /* ------------------------------------------------------------------ add / rnd: dispenser + rank threads */
 
-/* Take up to a->span_jobs consecutive jobs (cmd_add_worker's critical section, main.c:419-428, repeated).
- * Returns the number of jobs taken (0 = range exhausted) and the first job's start key. Consecutive jobs are
- * contiguous in units of the stride (job i starts at range_s + i*job*stride), which is what lets one
- * ecl_add_submit cover many of them; the last job overshoots range_e exactly like the reference (A.1). */
+/* next span of consecutive jobs from the shared plan (cmd_add_worker's critical section, main.c:419-428) */
 static uint64_t take_span(app *a, u256 start) {
-  uint64_t jobs = 0;
   pthread_mutex_lock(&a->mu);
-  const uint64_t visit = (a->job_keys + ECL_GROUP - 1) / ECL_GROUP * ECL_GROUP;
-  const uint64_t limit = visit == a->job_keys ? a->span_jobs : 1; /* a ragged job cannot be fused */
-  while (jobs < limit && !a->fatal) {
-    if (u256_cmp(a->next, a->range_e) >= 0 || u256_cmp(a->next, a->first) < 0) break;
-    if (jobs == 0) u256_copy(start, a->next);
-    u256 before;
-    u256_copy(before, a->next);
-    modn_add(a->next, a->next, a->job_inc);
-    jobs++;
-    if (u256_cmp(a->next, before) < 0) break; /* wrapped mod n: the next job is not contiguous with this span */
-  }
+  const uint64_t jobs = a->fatal ? 0 : jobplan_take(&a->plan, start);
   pthread_mutex_unlock(&a->mu);
   return jobs;
 }
@@ -290,7 +274,7 @@ static void *add_rank_main(void *p) {
   app *a = ((rank_arg *)p)->a;
   ecl_dev *dev = a->dev[((rank_arg *)p)->rank];
   hit_buf hb = {0};
-  const uint64_t visit = (a->job_keys + ECL_GROUP - 1) / ECL_GROUP * ECL_GROUP;
+  const uint64_t visit = a->plan.visit_keys;
   const uint64_t per_key = (a->flags & ECL_ENDO) ? 6 : 1;
   u256 start;
   uint64_t jobs;
@@ -303,44 +287,24 @@ static void *add_rank_main(void *p) {
     }
     if (collect_hits(a, dev, &hb, &n) != 0) break;
     if (report_add_hits(a, dev, &hb, n, start) != 0) break;
-    progress_add(a, jobs * a->job_keys * per_key); /* main.c:431 */
+    progress_add(a, jobs * a->plan.job_keys * per_key); /* main.c:431 */
   }
   free(hb.hits), free(hb.pks), free(hb.xy), free(hb.h33), free(hb.h65);
   return NULL;
 }
 
-static void run_add_ranks(app *a) {
+static void run_add_ranks(app *a, bool fixed_job) {
   pthread_t th[64];
   rank_arg arg[64];
-  u256 jk;
-  u256_set64(jk, a->job_keys);
-  modn_mul(a->job_inc, jk, a->stride); /* main.c:413-415 */
-  u256_copy(a->next, a->range_s);
-  u256_copy(a->first, a->range_s);
+  const char *env = getenv("ECLOOP_SPAN_JOBS"); /* default 2048 jobs = 2^32 keys per submit */
+  jobplan_init(&a->plan, a->range_s, a->range_e, a->ord_offs, fixed_job);
+  jobplan_choose_span(&a->plan, env ? strtoull(env, NULL, 10) : 2048, (unsigned)a->n_gpus);
   for (int r = 0; r < a->n_gpus; ++r) {
     arg[r].a = a, arg[r].rank = r;
     pthread_create(&th[r], NULL, add_rank_main, &arg[r]);
   }
   for (int r = 0; r < a->n_gpus; ++r) pthread_join(th[r], NULL);
   if (a->fatal) exit(1);
-}
-
-/* jobs fused per submit: large enough to fill a GPU (2^32 keys), small enough that a short range still spreads
- * over all ranks */
-static void choose_span(app *a) {
-  const char *env = getenv("ECLOOP_SPAN_JOBS");
-  uint64_t span = env ? strtoull(env, NULL, 10) : 2048;
-  if (span == 0) span = 1;
-  u256 r;
-  modn_sub(r, a->range_e, a->range_s);
-  const unsigned shift = 21 + a->ord_offs; /* keys per job * stride */
-  if (u256_bitlen(r) <= shift + 40 && shift < 256) {
-    u256 q = {0, 0, 0, 0};
-    for (unsigned i = shift; i < 256 && i - shift < 64; ++i) q[0] |= ((r[i / 64] >> (i % 64)) & 1ULL) << (i - shift);
-    const uint64_t total = q[0] + 1, per_rank = (total + (uint64_t)a->n_gpus - 1) / (uint64_t)a->n_gpus;
-    if (per_rank < span) span = per_rank;
-  }
-  a->span_jobs = span;
 }
 
 static void set_stride_all(app *a) { /* ctx_precompute_gpoints (main.c:219-246) now runs on each device */
@@ -352,13 +316,8 @@ static void set_stride_all(app *a) { /* ctx_precompute_gpoints (main.c:219-246) 
 
 static void cmd_add(app *a) { /* main.c:437-454 */
   set_stride_all(a);
-  u256 r;
-  modn_sub(r, a->range_e, a->range_s);
-  const bool small = !r[1] && !r[2] && !r[3] && r[0] < JOB_KEYS_MAX;
-  a->job_keys = small ? r[0] : JOB_KEYS_MAX;
-  choose_span(a);
   a->t_start = now_ms();
-  run_add_ranks(a);
+  run_add_ranks(a, false);
   finish(a);
 }
 
@@ -406,7 +365,6 @@ static void cmd_rnd(app *a) {
   if (a->ord_offs > 255 - a->ord_size) a->ord_offs = 255 - a->ord_size;
   printf("[RANDOM MODE] offs: %d ~ bits: %d\n\n", (int)a->ord_offs, (int)a->ord_size);
   set_stride_all(a);
-  a->job_keys = JOB_KEYS_MAX;
   a->t_start = now_ms();
   u256 lo, hi;
   u256_copy(lo, a->range_s);
@@ -430,8 +388,7 @@ static void cmd_rnd(app *a) {
     print_status_locked(a);
     pthread_mutex_unlock(&a->mu);
     const bool whole = u256_cmp(a->range_s, lo) == 0 && u256_cmp(a->range_e, hi) == 0;
-    choose_span(a);
-    run_add_ranks(a);
+    run_add_ranks(a, true);
     uint64_t dt = now_ms() - t0;
     if (dt < 1) dt = 1;
     clear_status_line();

@@ -303,3 +303,60 @@ def test_blf_gen_sizing_matches_reference(hl, tmp_path, n):
     _run(HOST / "ecloop", ["blf-gen", "-n", str(n), "-o", str(tmp_path / "a.blf")], h)
     _run(ref_bin, ["blf-gen", "-n", str(n), "-o", str(tmp_path / "b.blf")], h)
     assert (tmp_path / "a.blf").read_bytes() == (tmp_path / "b.blf").read_bytes()
+
+
+# ---------------------------------------------------------------- job plan (which keys an add / rnd run visits)
+
+
+class JobPlan(C.Structure):
+    _fields_ = [("next", C.c_uint64 * 4), ("first", C.c_uint64 * 4), ("range_e", C.c_uint64 * 4), ("stride", C.c_uint64 * 4),
+                ("job_inc", C.c_uint64 * 4), ("job_keys", C.c_uint64), ("visit_keys", C.c_uint64), ("span_jobs", C.c_uint64)]
+
+
+def c_job_plan(hl, rs, re_, offs, fixed=False, max_span=1, ranks=1):
+    hl.jobplan_take.restype = C.c_uint64
+    jp = JobPlan()
+    hl.jobplan_init(C.byref(jp), U(rs), U(re_), offs, fixed)
+    hl.jobplan_choose_span(C.byref(jp), C.c_uint64(max_span), ranks)
+    spans = []
+    while len(spans) < 100000:
+        start = U(0)
+        n = hl.jobplan_take(C.byref(jp), start)
+        if not n:
+            break
+        spans.append((I(start), int(n)))
+    return jp, spans
+
+
+@pytest.mark.parametrize("rs,re_,offs", [
+    (0x8000, 0xFFFF, 0), (0x8000, 0x8007, 0), (0x8000, 0x9FFF, 0), (0x8000, 0xFFFFFF, 0), (0x10000, 0x40FFFF, 0),
+    (2**70, 2**70 + 7, 7), (2**70, 2**70 + 2**30 - 1, 0), (2**70, 2**70 + 2**30, 0), (2**70 + 5, 2**70 + 2**26 + 11, 3),
+    (N - 2**24, N - 1, 0), (N - 2**23 - 5, N - 3, 0), (2**255, 2**255 + 2**28, 4), (0x100000, 0xFFFFFF, 3),
+])
+def test_job_plan_matches_reference_arithmetic(hl, rs, re_, offs):
+    """job starts / sizes equal the python mirror of main.c:405-454 (itself pinned to the reference's counters in
+    tests/test_host.py), and fused spans cover exactly the same jobs"""
+    import ecloop_b200.host as H
+
+    job, starts = H.job_plan(rs, re_, offs)
+    jp, spans = c_job_plan(hl, rs, re_, offs)
+    assert jp.job_keys == job and jp.visit_keys == (job + 2047) // 2048 * 2048
+    assert [s for s, n in spans] == starts and all(n == 1 for _, n in spans)
+    for max_span, ranks in ((2048, 1), (2048, 8), (3, 2)):
+        jp2, fused = c_job_plan(hl, rs, re_, offs, max_span=max_span, ranks=ranks)
+        flat = []
+        for s, n in fused:
+            assert n <= max_span
+            flat += [(s + i * job * (1 << offs)) % (1 << 256) for i in range(n)]  # contiguous inside a span
+        assert flat == starts
+        if job % 2048:
+            assert all(n == 1 for _, n in fused)
+        if len(starts) >= ranks and max_span == 2048:
+            assert len(fused) >= min(ranks, len(starts))  # a short range still spreads over all ranks
+
+
+def test_job_plan_rnd_uses_fixed_jobs(hl):
+    jp, spans = c_job_plan(hl, 0x8000000, 0x8000000 + 2**24 - 1, 0, fixed=True, max_span=2048, ranks=2)
+    assert jp.job_keys == 2**21 and sum(n for _, n in spans) == 8 and len(spans) >= 2
+    jp, spans = c_job_plan(hl, 0x800000, 0x800000 + 2**20 - 1, 0, fixed=True)  # window smaller than a job: one job
+    assert jp.job_keys == 2**21 and spans == [(0x800000, 1)]
