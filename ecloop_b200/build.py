@@ -1,7 +1,7 @@
 """Build libecloop_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot).
 
-Seven translation units compile in parallel: the host API + small kernels, and one fused add-kernel variant per
-address-type / endomorphism combination. Objects are cached under build/ keyed by a hash of all sources + flags.
+Thirteen translation units compile in parallel: the host API + small kernels, and one fused add-kernel variant per
+address-type / endomorphism combination, each for a filter in shared memory and for a filter in HBM. Objects are cached under build/ keyed by a hash of all sources + flags.
 """
 from __future__ import annotations
 
@@ -65,6 +65,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] =
     jobs = [(CSRC / "ecl_api.cu", OBJ / "ecl_api.o", [])]
     for v in ADD_VARIANTS:
         jobs.append((CSRC / "add_inst.cu", OBJ / f"add_inst_{v}.o", [f"-DADD_VARIANT={v}"]))
+        jobs.append((CSRC / "add_inst.cu", OBJ / f"add_inst_hbm_{v}.o", [f"-DADD_VARIANT={v}", "-DADD_HBM=1"]))
     dflags = [f"-D{d}" for d in defines]
 
     def compile_one(job):

@@ -19,11 +19,21 @@
 #define CAT2(a, b) a##b
 #define CAT(a, b) CAT2(a, b)
 
-cudaError_t CAT(ecl_add_launch_, ADD_VARIANT)(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
-#if ECL_ADD_SP && ADD_VARIANT == 1
-  auto fn = add_kernel_sp<ADD_H>;
+// -DADD_HBM=1 builds the instance for filters in HBM (asynchronous probe pipe, probe_pipe.cuh)
+#ifndef ADD_HBM
+#define ADD_HBM 0
+#endif
+#if ADD_HBM
+#define LAUNCH_NAME CAT(ecl_add_launch_hbm_, ADD_VARIANT)
 #else
-  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO>;
+#define LAUNCH_NAME CAT(ecl_add_launch_, ADD_VARIANT)
+#endif
+
+cudaError_t LAUNCH_NAME(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
+#if ECL_ADD_SP && ADD_VARIANT == 1
+  auto fn = add_kernel_sp<ADD_H, ADD_HBM != 0>;
+#else
+  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0>;
 #endif
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -2,6 +2,7 @@
 // (main.c:287-403, lib/addr.c:99-131, lib/utils.c:308-326) in one launch.
 #pragma once
 #include "common.cuh"
+#include "probe_pipe.cuh"
 
 struct AddParams {
   const u32 *cx, *cy;  // thread centres, SoA: limb l of thread t at [l*T + t]
@@ -14,7 +15,36 @@ struct AddParams {
   u32 groups_per_thread;  // consecutive groups of 2H keys owned by one thread
   u64 n_groups;           // groups in this launch
   u64 key_off0;           // index (in keys) of the first key of this launch inside the submitted span
+  CandQueue cand;         // HBM kernels only: where stage 1 of the asynchronous probe queues its candidates
 };
+
+// The probe pipe of a kernel instance: a ProbePipe in the dynamic shared memory behind the table for HBM filters,
+// an empty tag otherwise. `pipe` is what check_points / probe_hash take.
+#define PROBE_PIPE_SETUP(HBM_, SMEM_OFFSET_)                                                  \
+  __shared__ u32 cand_count;                                                                  \
+  typename PipeOf<HBM_>::type pipe;                                                           \
+  if (HBM_) {                                                                                 \
+    if (threadIdx.x == 0) cand_count = 0;                                                     \
+    __syncthreads();                                                                          \
+  }                                                                                           \
+  pipe_init(pipe, smem_raw + (SMEM_OFFSET_), &cand_count, p.bloom, p.cand);
+#define PROBE_PIPE_FINISH(HBM_) pipe_finish(pipe);
+
+template <bool HBM>
+struct PipeOf {
+  typedef NoPipe type;
+};
+template <>
+struct PipeOf<true> {
+  typedef ProbePipe<ADD_THREADS> type;
+};
+__device__ __forceinline__ void pipe_init(NoPipe &, unsigned char *, u32 *, const BloomView &, const CandQueue &) {}
+__device__ __forceinline__ void pipe_init(ProbePipe<ADD_THREADS> &pp, unsigned char *smem, u32 *cnt, const BloomView &bv,
+                                          const CandQueue &q) {
+  pp.init(smem, cnt, bv, q);
+}
+__device__ __forceinline__ void pipe_finish(NoPipe &) {}
+__device__ __forceinline__ void pipe_finish(ProbePipe<ADD_THREADS> &pp) { pp.finish(); }
 
 // Thread t owns the consecutive groups [t*c, (t+1)*c) of 2H keys. For one group with centre point
 // P = (start + (g*2H + H)*s)*G it forms every P +- (i+1)*s*G, i < H, sharing ONE field inversion through
@@ -23,7 +53,7 @@ struct AddParams {
 // rides in the same batch as element 0, so moving to the next group costs one affine addition and no
 // extra inversion (the reference pays a second inversion per group for that, main.c:400).
 // Key order inside a group matches the reference: K-H .. K-1, K, K+1 .. K+H-1 (main.c:363,391).
-template <int H, bool A33, bool A65, bool ENDO>
+template <int H, bool A33, bool A65, bool ENDO, bool HBM>
 __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const AddParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) u64 mbar;
@@ -43,6 +73,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
 
   BloomView bv = p.bloom;
   if (p.bloom_smem_words) bv.bits = sbloom;
+  PROBE_PIPE_SETUP(HBM, (H + 1) * 64)
 
   // Every thread of the CTA runs the same number of steps so that the CTA can sit behind barriers (lockstep,
   // see common.cuh): threads without work of their own (past T, or past the last group) run along on the last
@@ -106,7 +137,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
 #pragma unroll
       for (int l = 0; l < 8; ++l) x[1][l] = rx.v[l], y[1][l] = ry.v[l];
 
-      check_points<2, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x, y, off, active);
+      check_points<2, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x, y, off, active, pipe);
     }
 
     // ---- next group's centre: P + 2H*s*G with inv = 1/(step.x - px)
@@ -118,8 +149,8 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
       px = nx, py = ny;
     }
   }
+  PROBE_PIPE_FINISH(HBM)
 }
-
 
 // ---------------------------------------------------------------- K1-sp: software-pipelined addr33 variant
 // Same work as add_kernel<H, true, false, false>, restructured so that every basic block of the hot loop holds
@@ -145,7 +176,7 @@ static __device__ __noinline__ void check_one_slow(const BloomView &bv, const Hi
 // there is no field-only phase left: the group step is the element peeled FIRST (it is multiplied in last), which
 // makes the next centre known at the start of pass 2, and the prefixes go to the other half of a ping-pong scratch.
 // Elements of a group: f_i = table[i].x - px (i < H), f_H = step.x - px; scratch entry k holds q_k = f_0 ... f_{k-1}.
-template <int H>
+template <int H, bool HBM>
 __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(const AddParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) u64 mbar;
@@ -165,6 +196,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
 
   BloomView bv = p.bloom;
   if (p.bloom_smem_words) bv.bits = sbloom;
+  PROBE_PIPE_SETUP(HBM, (H + 1) * 64)
 
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 T = p.T;
@@ -251,7 +283,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       }
       {
         const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        if (bloom_has(bv, hh) && active) emit_hit(p.sink, kc - (u64)(i + 1), hh, 0, 0);
+        probe_hash(pipe, bv, p.sink, hh, kc - (u64)(i + 1), 0u, 0u, active);
       }
       // block Y: hash P + (i+1)G  ||  peel step i-1 and form P - iG
 #pragma unroll
@@ -268,7 +300,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       }
       {
         const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        if (bloom_has(bv, hh) && active && i != H - 1) emit_hit(p.sink, kc + (u64)(i + 1), hh, 0, 0);
+        probe_hash(pipe, bv, p.sink, hh, kc + (u64)(i + 1), 0u, 0u, active && i != H - 1);
       }
     }
     // ---- epilogue: step 0 (keys K-1 and K+1), the last two prefixes of the next group
@@ -288,5 +320,6 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     uint4 *sw = scr_cur;
     scr_cur = scr_nxt, scr_nxt = sw;
   }
+  PROBE_PIPE_FINISH(HBM)
 }
 

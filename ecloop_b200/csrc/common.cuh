@@ -86,9 +86,17 @@ __device__ __forceinline__ fe fe_beta() {
 // once. Emission order is restored on the host (ecl_collect sorts), so lanes may report in any order.
 // SYNC: CTA-barrier density inside the hashes (hash160.cuh); only legal when the whole CTA calls this in lockstep.
 // `active` masks the reporting of threads that only run along to keep the CTA in lockstep.
-template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0>
+// PIPE: nullptr_t-like tag type NoPipe (probe inline: filter in shared memory, or a parity kernel) or a ProbePipe
+// (probe_pipe.cuh: filter in HBM, probes in flight while the next hash is computed).
+struct NoPipe {};
+__device__ __forceinline__ void probe_hash(NoPipe &, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
+                                           u32 endo, u32 kind, bool active) {
+  if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, endo, kind);
+}
+
+template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0, class PIPE = NoPipe>
 __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
-                                             const u64 (&off)[NW], const bool active = true) {
+                                             const u64 (&off)[NW], const bool active, PIPE &pipe) {
   constexpr int NE = ENDO ? 6 : 1;
 #pragma unroll 1
   for (int e = 0; e < NE; ++e) {
@@ -119,7 +127,7 @@ __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink 
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (bloom_has(bv, hh) && active) emit_hit(sink, off[n], hh, (u32)e, 0);
+        probe_hash(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
       }
     }
     if (A65) {
@@ -128,9 +136,15 @@ __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink 
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (bloom_has(bv, hh) && active) emit_hit(sink, off[n], hh, (u32)e, 1);
+        probe_hash(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
       }
     }
   }
 }
 
+template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0>
+__device__ __forceinline__ void check_points(const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
+                                             const u64 (&off)[NW], const bool active = true) {
+  NoPipe none;
+  check_points<NW, A33, A65, ENDO, SYNC, NoPipe>(bv, sink, x, y, off, active, none);
+}

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct ecl_dev {
 
   u64 *bloom_bits = nullptr;
   u64 bloom_size = 0, bloom_magic = 0;
+  double bloom_fill = 0.5;  // fraction of set bits (measured by ecl_set_filter for filters that stay in HBM)
 
   u32 Tmax = 0;
   u32 *centres = nullptr;  // 16 x Tmax u32 (SoA x then y)
@@ -50,6 +52,12 @@ struct ecl_dev {
 
   fe *d_scalars = nullptr;
   u32 scalars_cap = 0;
+  // asynchronous probing of filters that do not fit shared memory (probe_pipe.cuh)
+  uint4 *cand_entries = nullptr;
+  u32 *cand_counts = nullptr;  // [sm_count] + 1 overflow flag
+  u64 cand_cap = 0;            // entries in total
+  bool force_inline = false;   // the last span overflowed the queue and is being redone with inline probes
+
   uint4 *mul_scratch = nullptr;  // 128 B per key of a mul batch (X, Y, Z, prefix product)
   u32 mul_scratch_cap = 0;
 
@@ -202,6 +210,7 @@ extern "C" void ecl_close(ecl_dev *dev) {
   cudaFree(dev->gtab), cudaFree(dev->bases), cudaFree(dev->add_table), cudaFree(dev->bloom_bits);
   cudaFree(dev->centres), cudaFree(dev->scratch), cudaFree(dev->d_hits), cudaFree(dev->d_hit_count);
   cudaFree(dev->d_scalars), cudaFree(dev->mul_scratch);
+  cudaFree(dev->cand_entries), cudaFree(dev->cand_counts);
   for (auto ev : dev->ev_pool) cudaEventDestroy(ev);
   if (dev->ev_begin) cudaEventDestroy(dev->ev_begin);
   if (dev->ev_end) cudaEventDestroy(dev->ev_end);
@@ -246,6 +255,18 @@ extern "C" int ecl_set_filter(ecl_dev *dev, const uint64_t *bits, uint64_t size_
   CK(cudaStreamSynchronize(dev->stream));
   dev->bloom_size = size_words;
   dev->bloom_magic = ~0ULL / size_words;
+  dev->bloom_fill = 0.5;
+  if (size_words * 8 > 64 * 1024) {  // stays in HBM: measure its fill for the candidate-queue planner
+    unsigned long long *d_total = nullptr, total = 0;
+    CK(cudaMalloc(&d_total, sizeof total));
+    CK(cudaMemsetAsync(d_total, 0, sizeof total, dev->stream));
+    bloom_popcount_kernel<<<dev->sm_count * 8, 256, 0, dev->stream>>>(dev->bloom_bits, size_words, d_total);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, dev->stream));
+    CK(cudaStreamSynchronize(dev->stream));
+    cudaFree(d_total);
+    dev->bloom_fill = (double)total / ((double)size_words * 64.0);
+  }
   return ECL_OK;
 }
 
@@ -288,17 +309,38 @@ static int ensure_add_resources(ecl_dev *dev) {
 // the six add_kernel variants live in add_inst.cu, one translation unit each (parallel build)
 #define DECL_ADD(v) cudaError_t ecl_add_launch_##v(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream);
 DECL_ADD(1) DECL_ADD(2) DECL_ADD(3) DECL_ADD(5) DECL_ADD(6) DECL_ADD(7)
+DECL_ADD(hbm_1) DECL_ADD(hbm_2) DECL_ADD(hbm_3) DECL_ADD(hbm_5) DECL_ADD(hbm_6) DECL_ADD(hbm_7)
 typedef cudaError_t (*add_launch_fn)(const AddParams &, unsigned, unsigned, cudaStream_t);
-static add_launch_fn pick_add_kernel(u32 flags) {
+static add_launch_fn pick_add_kernel(u32 flags, bool hbm) {
   switch (flags & (ECL_A33 | ECL_A65 | ECL_ENDO)) {
-  case 1: return ecl_add_launch_1;
-  case 2: return ecl_add_launch_2;
-  case 3: return ecl_add_launch_3;
-  case 5: return ecl_add_launch_5;
-  case 6: return ecl_add_launch_6;
-  case 7: return ecl_add_launch_7;
+  case 1: return hbm ? ecl_add_launch_hbm_1 : ecl_add_launch_1;
+  case 2: return hbm ? ecl_add_launch_hbm_2 : ecl_add_launch_2;
+  case 3: return hbm ? ecl_add_launch_hbm_3 : ecl_add_launch_3;
+  case 5: return hbm ? ecl_add_launch_hbm_5 : ecl_add_launch_5;
+  case 6: return hbm ? ecl_add_launch_hbm_6 : ecl_add_launch_6;
+  case 7: return hbm ? ecl_add_launch_hbm_7 : ecl_add_launch_7;
   default: return nullptr;
   }
+}
+
+// The candidate queue of the asynchronous probe: as large as is reasonable (the add kernel wants >= 75 776 threads
+// x 2048 keys per launch and fill^2 of all hashes become candidates), sized once per device.
+static int ensure_cand_queue(ecl_dev *dev) {
+  if (dev->cand_entries) return ECL_OK;
+  u64 want = 1ull << 29;  // 16 GB
+  if (const char *env = getenv("ECLOOP_B200_CAND_LOG2")) want = 1ull << std::min(31, std::max(8, atoi(env)));  // test hook
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  while (want > 256 && want * 32 > free_b / 3) want >>= 1;
+  for (;; want >>= 1) {
+    if (cudaMalloc(&dev->cand_entries, want * 32) == cudaSuccess) break;
+    cudaGetLastError();
+    dev->cand_entries = nullptr;
+    if (want <= 256) return fail(dev, ECL_E_CUDA, "cannot allocate the candidate queue");
+  }
+  dev->cand_cap = want;
+  CK(cudaMalloc(&dev->cand_counts, ((size_t)dev->sm_count + 1) * sizeof(u32)));
+  return ECL_OK;
 }
 
 static cudaEvent_t next_event(ecl_dev *dev) {
@@ -313,13 +355,28 @@ static cudaEvent_t next_event(ecl_dev *dev) {
 // Queue the launches covering groups [g_begin, g_end) of the pending span. max_groups_per_launch bounds one launch.
 static int launch_add(ecl_dev *dev, u64 g_begin, u64 g_end, u64 max_groups_per_launch, bool drain_each,
                       std::vector<ecl_hit> *drain_to) {
-  add_launch_fn fn = pick_add_kernel(dev->p_flags);
-  if (!fn) return fail(dev, ECL_E_ARG, "flags select no address type");
   const u32 smem_table = (ADD_H + 1) * 64;
-  // the filter rides in shared memory when two CTAs per SM still fit (227 KB per SM)
+  // the filter rides in shared memory when it fits beside the table; otherwise it stays in HBM and is probed
+  // asynchronously (probe_pipe.cuh) unless a span is being redone after a candidate-queue overflow, or drained
+  // launch by launch for a dense filter (then the inline probe is exact and simple)
   const u64 bloom_bytes = (dev->bloom_size + 1) / 2 * 16;
   const bool bloom_smem = smem_table + bloom_bytes <= 110u * 1024u;
-  const u32 smem = smem_table + (bloom_smem ? (u32)bloom_bytes : 0u);
+  static const bool no_pipe = getenv("ECLOOP_B200_INLINE_PROBE") != nullptr;  // measurement hook: probe HBM filters inline
+  const bool hbm = !bloom_smem && !dev->force_inline && !drain_each && !no_pipe;
+  add_launch_fn fn = pick_add_kernel(dev->p_flags, hbm);
+  if (!fn) return fail(dev, ECL_E_ARG, "flags select no address type");
+  const u32 smem = smem_table + (bloom_smem ? (u32)bloom_bytes : 0u) + (hbm ? ProbePipe<ADD_THREADS>::BYTES : 0u);
+  if (hbm) {
+    int rc = ensure_cand_queue(dev);
+    if (rc) return rc;
+    // stage 1 passes fill^2 of the hashes: a launch is sized so that the expected candidates use 2/3 of the queue
+    const u32 hashes_per_key = ((dev->p_flags & ECL_A33) ? 1u : 0u) + ((dev->p_flags & ECL_A65) ? 1u : 0u);
+    const double hashes_per_group = (double)GROUP_KEYS * hashes_per_key * ((dev->p_flags & ECL_ENDO) ? 6.0 : 1.0);
+    const double per_group = std::max(1.0, hashes_per_group * dev->bloom_fill * dev->bloom_fill * 1.5);
+    u64 fit = std::max<u64>(1, (u64)((double)dev->cand_cap / per_group));
+    if (fit >= dev->Tmax) fit -= fit % dev->Tmax;  // whole rounds of the grid: every SM keeps its CTA busy
+    max_groups_per_launch = std::min(max_groups_per_launch, fit);
+  }
 
   u64 g = g_begin;
   while (g < g_end) {
@@ -345,10 +402,22 @@ static int launch_add(ecl_dev *dev, u64 g_begin, u64 g_end, u64 max_groups_per_l
     ap.bloom_smem_words = bloom_smem ? (u32)dev->bloom_size : 0u;
     ap.sink.hits = dev->d_hits, ap.sink.count = dev->d_hit_count, ap.sink.cap = dev->hit_cap;
     ap.T = T, ap.groups_per_thread = (u32)c, ap.n_groups = L, ap.key_off0 = g * GROUP_KEYS;
+    const u32 grid = (T + ADD_THREADS - 1) / ADD_THREADS;
+    if (hbm) {
+      ap.cand.entries = dev->cand_entries, ap.cand.counts = dev->cand_counts;
+      ap.cand.overflow = dev->cand_counts + dev->sm_count;
+      ap.cand.cap_per_cta = (u32)std::min<u64>(dev->cand_cap / grid, 0xffffffffu);
+      CK(cudaMemsetAsync(dev->cand_counts, 0, (size_t)dev->sm_count * sizeof(u32), dev->stream));  // not the flag
+    }
     cudaEvent_t e0 = next_event(dev), e1 = next_event(dev);
     if (!e0 || !e1) return fail(dev, ECL_E_CUDA, "cudaEventCreate failed");
     CK(cudaEventRecord(e0, dev->stream));
-    CK(fn(ap, (T + ADD_THREADS - 1) / ADD_THREADS, smem, dev->stream));
+    CK(fn(ap, grid, smem, dev->stream));
+    if (hbm) {  // stage 2: the full test on what stage 1 queued
+      cand_verify_kernel<<<dim3(32, grid), 256, 0, dev->stream>>>(ap.cand, ap.bloom, ap.sink);
+      CK(cudaGetLastError());
+      dev->launches++;
+    }
     CK(cudaEventRecord(e1, dev->stream));
     dev->launches += 2;
     g += L;
@@ -382,6 +451,8 @@ extern "C" int ecl_add_submit(ecl_dev *dev, const uint64_t start_pk[4], uint64_t
   memcpy(dev->p_start, start_pk, 32);
   dev->p_keys = n_keys, dev->p_flags = flags;
   CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
+  dev->force_inline = false;
+  if (dev->cand_counts) CK(cudaMemsetAsync(dev->cand_counts + dev->sm_count, 0, sizeof(u32), dev->stream));
   const u64 n_groups = n_keys / GROUP_KEYS;
   rc = launch_add(dev, 0, n_groups, (u64)dev->Tmax * dev->groups_per_thread, false, nullptr);
   if (rc) return rc;
@@ -487,6 +558,22 @@ extern "C" int ecl_collect(ecl_dev *dev, ecl_hit *hits, uint32_t cap, uint32_t *
       dev->last_hot_ms += ms;
     }
     dev->last_launches = dev->launches;
+    if (dev->pending == 1 && dev->cand_counts && !dev->force_inline) {
+      // the asynchronous probe's candidate queue overflowed (a filter far denser than a bloom filter should be):
+      // nothing may be lost, so the span is redone with the probes inline
+      u32 ovf = 0;
+      CK(cudaMemcpy(&ovf, dev->cand_counts + dev->sm_count, sizeof ovf, cudaMemcpyDeviceToHost));
+      if (ovf) {
+        dev->force_inline = true;
+        CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
+        int rc2 = launch_add(dev, 0, dev->p_keys / GROUP_KEYS, (u64)dev->Tmax * dev->groups_per_thread, false, nullptr);
+        if (rc2) {
+          dev->pending = 0;
+          return rc2;
+        }
+        CK(cudaStreamSynchronize(dev->stream));
+      }
+    }
     u32 cnt = 0;
     CK(cudaMemcpy(&cnt, dev->d_hit_count, sizeof cnt, cudaMemcpyDeviceToHost));
     dev->result.clear();

@@ -1,0 +1,126 @@
+// probe_pipe.cuh — asynchronous bloom probing for filters that live in HBM (`.blf` files of hundreds of MB to GBs).
+//
+// blf_has (lib/utils.c:308-326) is a chain of up to 20 dependent random 8-byte reads with early exit. With the
+// filter in shared memory that is a few cycles; in HBM every read is ~1 us, and because the fused add kernel runs
+// its 16 warps in lockstep nobody hides it: the inline probe costs 30 % of the kernel (profiles/r01_d_large_bloom.txt).
+// Here the kernel never waits for the filter:
+//   stage 1 (in the add kernel)  the first TWO probe words of a hash are fetched with cp.async straight into shared
+//                                memory (no register, no stall) and looked at PP_DEPTH hashes later; a hash whose
+//                                two bits are set (fill^2 of them) goes to a per-CTA candidate queue in HBM;
+//   stage 2 (cand_verify_kernel) one thread per candidate runs the full 20-probe test at full occupancy and
+//                                reports the hits.
+// The decision is blf_has's, bit for bit: stage 1 only drops hashes that blf_has would drop at probe 1 or 2.
+#pragma once
+#include "common.cuh"
+
+#define PP_DEPTH 2  // hashes in flight per thread
+
+struct CandQueue {
+  uint4 *entries;   // n_cta regions of cap_per_cta candidates, 32 B each (same layout as ecl_hit)
+  u32 *counts;      // candidates pushed by each CTA (may exceed cap_per_cta: then *overflow is set)
+  u32 *overflow;
+  u32 cap_per_cta;
+};
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Per-thread view of the CTA's pending-probe storage in shared memory. Layout (conflict-free, thread-minor):
+//   u64 words[PP_DEPTH][2][THREADS]     the two probe words of a pending hash
+//   u32 meta [PP_DEPTH][8][THREADS]     h[0..4], key_off lo/hi, endo | kind << 8 | active << 16
+template <int THREADS>
+struct ProbePipe {
+  static constexpr u32 BYTES = PP_DEPTH * (2 * 8 + 8 * 4) * THREADS;
+  u64 *words;
+  u32 *meta;
+  u32 *cta_count;  // shared
+  BloomView bv;    // the filter in global memory
+  CandQueue q;
+  u32 n;           // hashes submitted so far by this thread
+
+  __device__ __forceinline__ void init(unsigned char *smem, u32 *count, const BloomView &b, const CandQueue &cq) {
+    words = reinterpret_cast<u64 *>(smem) + threadIdx.x;
+    meta = reinterpret_cast<u32 *>(smem + PP_DEPTH * 2 * 8 * THREADS) + threadIdx.x;
+    cta_count = count, bv = b, q = cq, n = 0;
+  }
+
+  __device__ __forceinline__ void retire(u32 slot) {
+    const u64 w0 = words[(slot * 2 + 0) * THREADS], w1 = words[(slot * 2 + 1) * THREADS];
+    const u32 *m = meta + slot * 8 * THREADS;
+    const u32 h0 = m[0], h3 = m[3 * THREADS], flags = m[7 * THREADS];
+    // bit positions of probes 1 and 2 (shift 24): v mod 64 = low 6 bits of (a2 >> 24) resp. (a3 >> 24)
+    const u32 b0 = (h3 >> 24) & 63u, b1 = (h0 >> 24) & 63u;
+    if ((((w0 >> b0) & (w1 >> b1)) & 1ull) && (flags >> 16)) {
+      const u32 idx = atomicAdd(cta_count, 1u);
+      if (idx < q.cap_per_cta) {
+        uint4 *o = q.entries + ((size_t)blockIdx.x * q.cap_per_cta + idx) * 2;
+        o[0] = make_uint4(m[5 * THREADS], m[6 * THREADS], h0, m[1 * THREADS]);
+        o[1] = make_uint4(m[2 * THREADS], h3, m[4 * THREADS], flags & 0xffffu);
+      } else {
+        *q.overflow = 1u;
+      }
+    }
+  }
+
+  // hand one hash to the pipe; the verdict on the hash submitted PP_DEPTH calls ago is taken first
+  __device__ __forceinline__ void submit(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
+    const u32 slot = n % PP_DEPTH;
+    if (n >= PP_DEPTH) {
+      cp_async_wait<PP_DEPTH - 1>();
+      retire(slot);
+    }
+    const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
+    const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
+    cp_async_8(&words[(slot * 2 + 0) * THREADS], bv.bits + bloom_word_index(v0 >> 6, bv.size, bv.magic));
+    cp_async_8(&words[(slot * 2 + 1) * THREADS], bv.bits + bloom_word_index(v1 >> 6, bv.size, bv.magic));
+    cp_async_commit();
+    u32 *m = meta + slot * 8 * THREADS;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) m[i * THREADS] = h[i];
+    m[5 * THREADS] = (u32)off, m[6 * THREADS] = (u32)(off >> 32);
+    m[7 * THREADS] = endo | (kind << 8) | ((active ? 1u : 0u) << 16);
+    ++n;
+  }
+
+  // end of the kernel: take the verdict on everything still in flight and publish the CTA's candidate count
+  __device__ __forceinline__ void finish() {
+    cp_async_wait<0>();
+    const u32 pending = n < PP_DEPTH ? n : PP_DEPTH;
+    for (u32 k = 0; k < pending; ++k) retire((n - 1 - k) % PP_DEPTH);
+    __syncthreads();
+    if (threadIdx.x == 0) q.counts[blockIdx.x] = *cta_count;
+  }
+};
+
+template <int THREADS>
+__device__ __forceinline__ void probe_hash(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
+                                           u64 off, u32 endo, u32 kind, bool active) {
+  pipe.submit(hh, off, endo, kind, active);
+}
+
+// stage 2: the full blf_has on every queued candidate. grid = (x, number of source CTAs)
+static __global__ void __launch_bounds__(256) cand_verify_kernel(const CandQueue q, const BloomView bv, const HitSink sink) {
+  const u32 src = blockIdx.y;
+  u32 cnt = q.counts[src];
+  if (cnt > q.cap_per_cta) cnt = q.cap_per_cta;
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+    const uint4 *e = q.entries + ((size_t)src * q.cap_per_cta + j) * 2;
+    const uint4 a = e[0], b = e[1];
+    const u32 hh[5] = {a.z, a.w, b.x, b.y, b.z};
+    if (bloom_has(bv, hh)) emit_hit(sink, (u64)a.x | (u64)a.y << 32, hh, b.w & 0xffu, (b.w >> 8) & 0xffu);
+  }
+}
+
+// set bits of the filter (grid-stride popcount): the launch planner sizes the candidate queue by fill^2
+static __global__ void __launch_bounds__(256) bloom_popcount_kernel(const u64 *bits, u64 n, unsigned long long *total) {
+  unsigned long long acc = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) acc += __popcll(bits[i]);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}

