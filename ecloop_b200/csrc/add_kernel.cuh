@@ -109,10 +109,20 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
     fe inv = fe_inv(acc);  // 1 / (e_0 ... e_H)
 
     // ---- pass 2: peel the inverses off from the far end; two points per step
+    // With the filter in HBM thousands of TLB-missing probe fetches are in flight per SM and a scratch load issued
+    // behind them takes ~10 us: there the prefix of the NEXT step is fetched before this step's hashes.
+    fe pre_next = fe_from_u4(scr[(size_t)(2 * (H - 1)) * TS], scr[(size_t)(2 * (H - 1) + 1) * TS]);
 #pragma unroll 1
     for (int i = H - 1; i >= 0; --i) {
       if (ECL_HASH_SYNC) __syncthreads();
-      const fe pre = fe_from_u4(scr[(size_t)(2 * i) * TS], scr[(size_t)(2 * i + 1) * TS]);  // e_0 ... e_i
+      fe pre;  // e_0 ... e_i
+      if (HBM) {
+        pre = pre_next;
+        const int j = i > 0 ? i - 1 : 0;
+        pre_next = fe_from_u4(scr[(size_t)(2 * j) * TS], scr[(size_t)(2 * j + 1) * TS]);
+      } else {
+        pre = fe_from_u4(scr[(size_t)(2 * i) * TS], scr[(size_t)(2 * i + 1) * TS]);
+      }
       const fe gx = fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]);
       const fe gy = fe_from_u4(tab[i * 4 + 2], tab[i * 4 + 3]);
       const fe inv_i = fe_mul(inv, pre);  // 1 / (gx - px)

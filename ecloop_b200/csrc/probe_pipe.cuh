@@ -22,8 +22,10 @@ struct CandQueue {
   u32 cap_per_cta;
 };
 
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+// 16 bytes global -> shared without touching a register; .cg keeps the line out of L1, so a probe costs one 32 B
+// DRAM sector (with .ca every probe pulled a whole 128 B line: 267 B/key of DRAM reads in the first version)
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -31,37 +33,40 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Per-thread view of the CTA's pending-probe storage in shared memory. Layout (conflict-free, thread-minor):
-//   u64 words[PP_DEPTH][2][THREADS]     the two probe words of a pending hash
-//   u32 meta [PP_DEPTH][8][THREADS]     h[0..4], key_off lo/hi, endo | kind << 8 | active << 16
+// Per-thread view of the CTA's pending-probe storage in shared memory. Layout (128-bit accesses, thread-minor):
+//   uint4 probe[PP_DEPTH][2][THREADS]   the aligned 16 bytes around each of the two probe words
+//   uint4 meta [PP_DEPTH][2][THREADS]   {h0,h1,h2,h3}, {h4, key_off lo, key_off hi, flags}
+// flags: endo | kind << 8 | active << 16 | (bit position, which half) of probe 1 << 17 | same of probe 2 << 24
 template <int THREADS>
 struct ProbePipe {
-  static constexpr u32 BYTES = PP_DEPTH * (2 * 8 + 8 * 4) * THREADS;
-  u64 *words;
-  u32 *meta;
+  static constexpr u32 BYTES = PP_DEPTH * 4 * 16 * THREADS;
+  uint4 *probe;
+  uint4 *meta;
   u32 *cta_count;  // shared
   BloomView bv;    // the filter in global memory
   CandQueue q;
   u32 n;           // hashes submitted so far by this thread
 
   __device__ __forceinline__ void init(unsigned char *smem, u32 *count, const BloomView &b, const CandQueue &cq) {
-    words = reinterpret_cast<u64 *>(smem) + threadIdx.x;
-    meta = reinterpret_cast<u32 *>(smem + PP_DEPTH * 2 * 8 * THREADS) + threadIdx.x;
+    probe = reinterpret_cast<uint4 *>(smem) + threadIdx.x;
+    meta = probe + PP_DEPTH * 2 * THREADS;
     cta_count = count, bv = b, q = cq, n = 0;
   }
 
   __device__ __forceinline__ void retire(u32 slot) {
-    const u64 w0 = words[(slot * 2 + 0) * THREADS], w1 = words[(slot * 2 + 1) * THREADS];
-    const u32 *m = meta + slot * 8 * THREADS;
-    const u32 h0 = m[0], h3 = m[3 * THREADS], flags = m[7 * THREADS];
-    // bit positions of probes 1 and 2 (shift 24): v mod 64 = low 6 bits of (a2 >> 24) resp. (a3 >> 24)
-    const u32 b0 = (h3 >> 24) & 63u, b1 = (h0 >> 24) & 63u;
-    if ((((w0 >> b0) & (w1 >> b1)) & 1ull) && (flags >> 16)) {
+    const uint4 m1 = meta[(slot * 2 + 1) * THREADS];
+    const u32 flags = m1.w;
+    // the probed 64-bit word is the low or high half of the fetched 16 bytes
+    const u32 p0 = (flags >> 17) & 127u, p1 = (flags >> 24) & 127u;
+    const u64 *w = reinterpret_cast<const u64 *>(probe + (slot * 2) * THREADS);
+    const u64 w0 = w[p0 >> 6], w1 = reinterpret_cast<const u64 *>(probe + (slot * 2 + 1) * THREADS)[p1 >> 6];
+    if ((((w0 >> (p0 & 63u)) & (w1 >> (p1 & 63u))) & 1ull) && ((flags >> 16) & 1u)) {
+      const uint4 m0 = meta[(slot * 2) * THREADS];
       const u32 idx = atomicAdd(cta_count, 1u);
       if (idx < q.cap_per_cta) {
         uint4 *o = q.entries + ((size_t)blockIdx.x * q.cap_per_cta + idx) * 2;
-        o[0] = make_uint4(m[5 * THREADS], m[6 * THREADS], h0, m[1 * THREADS]);
-        o[1] = make_uint4(m[2 * THREADS], h3, m[4 * THREADS], flags & 0xffffu);
+        o[0] = make_uint4(m1.y, m1.z, m0.x, m0.y);
+        o[1] = make_uint4(m0.z, m0.w, m1.x, flags & 0xffffu);
       } else {
         *q.overflow = 1u;
       }
@@ -77,14 +82,14 @@ struct ProbePipe {
     }
     const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
     const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
-    cp_async_8(&words[(slot * 2 + 0) * THREADS], bv.bits + bloom_word_index(v0 >> 6, bv.size, bv.magic));
-    cp_async_8(&words[(slot * 2 + 1) * THREADS], bv.bits + bloom_word_index(v1 >> 6, bv.size, bv.magic));
+    const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
+    cp_async_16(&probe[(slot * 2 + 0) * THREADS], bv.bits + (i0 & ~1ull));
+    cp_async_16(&probe[(slot * 2 + 1) * THREADS], bv.bits + (i1 & ~1ull));
     cp_async_commit();
-    u32 *m = meta + slot * 8 * THREADS;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) m[i * THREADS] = h[i];
-    m[5 * THREADS] = (u32)off, m[6 * THREADS] = (u32)(off >> 32);
-    m[7 * THREADS] = endo | (kind << 8) | ((active ? 1u : 0u) << 16);
+    const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
+    meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
+    meta[(slot * 2 + 1) * THREADS] =
+        make_uint4(h[4], (u32)off, (u32)(off >> 32), endo | (kind << 8) | ((active ? 1u : 0u) << 16) | (p0 << 17) | (p1 << 24));
     ++n;
   }
 
