@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       }
       {
         const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        probe_hash(pipe, bv, p.sink, hh, kc - (u64)(i + 1), 0u, 0u, active);
+        probe_hash_dyn(pipe, bv, p.sink, hh, kc - (u64)(i + 1), 0u, 0u, active);
       }
       // block Y: hash P + (i+1)G  ||  peel step i-1 and form P - iG
 #pragma unroll
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       }
       {
         const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        probe_hash(pipe, bv, p.sink, hh, kc + (u64)(i + 1), 0u, 0u, active && i != H - 1);
+        probe_hash_dyn(pipe, bv, p.sink, hh, kc + (u64)(i + 1), 0u, 0u, active && i != H - 1);
       }
     }
     // ---- epilogue: step 0 (keys K-1 and K+1), the last two prefixes of the next group

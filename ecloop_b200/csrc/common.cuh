@@ -89,13 +89,16 @@ __device__ __forceinline__ fe fe_beta() {
 // PIPE: nullptr_t-like tag type NoPipe (probe inline: filter in shared memory, or a parity kernel) or a ProbePipe
 // (probe_pipe.cuh: filter in HBM, probes in flight while the next hash is computed).
 struct NoPipe {};
+// SLOT: which of the pipe's two in-flight slots this call site uses (call sites must alternate 0, 1, 0, 1, ...)
+template <u32 SLOT>
 __device__ __forceinline__ void probe_hash(NoPipe &, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
                                            u32 endo, u32 kind, bool active) {
   if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, endo, kind);
 }
 
 template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0, class PIPE = NoPipe>
-__device__ __forceinline__ void check_points(const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
+__device__ __forceinline__ void check_points(  // with a ProbePipe NW must be 2: lane n uses slot n
+    const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
                                              const u64 (&off)[NW], const bool active, PIPE &pipe) {
   constexpr int NE = ENDO ? 6 : 1;
 #pragma unroll 1
@@ -127,7 +130,8 @@ __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink 
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        probe_hash(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
+        if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
+        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
       }
     }
     if (A65) {
@@ -136,7 +140,8 @@ __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink 
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        probe_hash(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
+        if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
+        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
       }
     }
   }

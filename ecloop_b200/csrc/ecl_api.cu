@@ -185,6 +185,8 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
     if (prop.major < 10) return fail(dev, ECL_E_NODEV, "device %d is sm_%d%d; this build targets sm_100a only", ordinal, prop.major, prop.minor);
     dev->sm_count = prop.multiProcessorCount;
     dev->Tmax = (u32)dev->sm_count * ADD_THREADS * ADD_MIN_BLOCKS;
+    // random 8-byte filter probes should cost one 32 B sector of DRAM traffic, not a 128 B line
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     CK(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
     dev->stream = dev->own_stream;
     CK(cudaEventCreate(&dev->ev_begin));

@@ -24,7 +24,22 @@ struct CandQueue {
 
 // 16 bytes global -> shared without touching a register; .cg keeps the line out of L1, so a probe costs one 32 B
 // DRAM sector (with .ca every probe pulled a whole 128 B line: 267 B/key of DRAM reads in the first version)
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+// The probes stream through a filter far larger than L2: they are marked evict-first so that they do not push the
+// kernel's own instructions out of L2 (an ncu capture of the `-a cu` instance showed 5.6 no_instruction stalls per
+// issued instruction with plain probes: the 230 KB loop body was being refetched from DRAM).
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// dst is a 32-bit shared-memory address held in ONE opaque register (ProbePipe::init): when ptxas could see it as
+// uniform base + thread offset it emitted LDGSTS [R+UR+imm], desc[UR] with undefined uniform registers for some
+// instances (CUDA 12.9, "illegal instruction" at run time).
+__device__ __forceinline__ void cp_async_16(u32 smem_dst, const void *gmem_src, u64 policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(policy) : "memory");
+}
+// plain form (no cache hint), destination given as a pointer
+__device__ __forceinline__ void cp_async_16_plain(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -46,11 +61,15 @@ struct ProbePipe {
   BloomView bv;    // the filter in global memory
   CandQueue q;
   u32 n;           // hashes submitted so far by this thread
+  u64 policy;      // L2 evict-first for the probe fetches
+  u32 probe_s32;   // shared-memory address of probe[0] for this thread, opaque to the compiler
 
   __device__ __forceinline__ void init(unsigned char *smem, u32 *count, const BloomView &b, const CandQueue &cq) {
     probe = reinterpret_cast<uint4 *>(smem) + threadIdx.x;
     meta = probe + PP_DEPTH * 2 * THREADS;
     cta_count = count, bv = b, q = cq, n = 0;
+    policy = l2_evict_first_policy();
+    asm("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(probe_s32) : "l"(probe));
   }
 
   __device__ __forceinline__ void retire(u32 slot) {
@@ -73,8 +92,33 @@ struct ProbePipe {
     }
   }
 
-  // hand one hash to the pipe; the verdict on the hash submitted PP_DEPTH calls ago is taken first
+  // hand one hash to the pipe; the verdict on the hash that used this slot before (PP_DEPTH submissions ago) is
+  // taken first. Call sites alternate the slots 0, 1, 0, 1, ... with a compile-time SLOT, which keeps every
+  // shared-memory address of the pipe in the form [register + immediate].
+  template <u32 slot>
   __device__ __forceinline__ void submit(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
+    static_assert(slot < PP_DEPTH, "slot out of range");
+    if (n >= PP_DEPTH) {
+      cp_async_wait<PP_DEPTH - 1>();
+      retire(slot);
+    }
+    const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
+    const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
+    const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
+    cp_async_16(probe_s32 + (slot * 2 + 0) * THREADS * 16, bv.bits + (i0 & ~1ull), policy);
+    cp_async_16(probe_s32 + (slot * 2 + 1) * THREADS * 16, bv.bits + (i1 & ~1ull), policy);
+    cp_async_commit();
+    const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
+    meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
+    meta[(slot * 2 + 1) * THREADS] =
+        make_uint4(h[4], (u32)off, (u32)(off >> 32), endo | (kind << 8) | ((active ? 1u : 0u) << 16) | (p0 << 17) | (p1 << 24));
+    ++n;
+  }
+
+  // Variant for the software-pipelined kernel: run-time slot, no cache hint. That kernel's 7 000-instruction basic
+  // blocks are sensitive to what ptxas makes of any change here (5 840 vs 4 560 Mkeys/s for equivalent forms), its
+  // loop is small enough to stay in L2 beside the probe traffic, and this is the form measured at 5 840.
+  __device__ __forceinline__ void submit_dyn(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
     const u32 slot = n % PP_DEPTH;
     if (n >= PP_DEPTH) {
       cp_async_wait<PP_DEPTH - 1>();
@@ -83,8 +127,8 @@ struct ProbePipe {
     const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
     const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
     const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
-    cp_async_16(&probe[(slot * 2 + 0) * THREADS], bv.bits + (i0 & ~1ull));
-    cp_async_16(&probe[(slot * 2 + 1) * THREADS], bv.bits + (i1 & ~1ull));
+    cp_async_16_plain(&probe[(slot * 2 + 0) * THREADS], bv.bits + (i0 & ~1ull));
+    cp_async_16_plain(&probe[(slot * 2 + 1) * THREADS], bv.bits + (i1 & ~1ull));
     cp_async_commit();
     const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
     meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
@@ -96,17 +140,28 @@ struct ProbePipe {
   // end of the kernel: take the verdict on everything still in flight and publish the CTA's candidate count
   __device__ __forceinline__ void finish() {
     cp_async_wait<0>();
-    const u32 pending = n < PP_DEPTH ? n : PP_DEPTH;
-    for (u32 k = 0; k < pending; ++k) retire((n - 1 - k) % PP_DEPTH);
+    if (n >= 1) retire((n - 1) % PP_DEPTH);
+    if (n >= 2) retire((n - 2) % PP_DEPTH);
+    static_assert(PP_DEPTH == 2, "finish() retires exactly two slots");
     __syncthreads();
     if (threadIdx.x == 0) q.counts[blockIdx.x] = *cta_count;
   }
 };
 
-template <int THREADS>
+template <u32 SLOT, int THREADS>
 __device__ __forceinline__ void probe_hash(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
                                            u64 off, u32 endo, u32 kind, bool active) {
-  pipe.submit(hh, off, endo, kind, active);
+  pipe.template submit<SLOT>(hh, off, endo, kind, active);
+}
+
+template <int THREADS>
+__device__ __forceinline__ void probe_hash_dyn(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
+                                               u64 off, u32 endo, u32 kind, bool active) {
+  pipe.submit_dyn(hh, off, endo, kind, active);
+}
+__device__ __forceinline__ void probe_hash_dyn(NoPipe &np, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
+                                               u32 endo, u32 kind, bool active) {
+  probe_hash<0>(np, bv, sink, hh, off, endo, kind, active);
 }
 
 // stage 2: the full blf_has on every queued candidate. grid = (x, number of source CTAs)
