@@ -1,6 +1,6 @@
-// add_inst.cu — one add_kernel variant per translation unit (-DADD_VARIANT=0..5) so the six address-type /
-// endomorphism combinations compile in parallel. Variant = (A33 ? 1 : 0) | (A65 ? 2 : 0) | (ENDO ? 4 : 0), minus 1
-// for the two invalid "no address type" codes (see add_variant_index in ecl_api.cu).
+// add_inst.cu — one instance of the fused add kernel per translation unit so that the twelve of them compile in
+// parallel: -DADD_VARIANT = (A33 ? 1 : 0) | (A65 ? 2 : 0) | (ENDO ? 4 : 0) (1, 2, 3, 5, 6, 7: ecl_api.cu pick_add_kernel),
+// each with -DADD_HBM=0 (filter in shared memory, inline probes) and -DADD_HBM=1 (filter in HBM, probe pipe).
 #include <cuda_runtime.h>
 
 #include "add_kernel.cuh"

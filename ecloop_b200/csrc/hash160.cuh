@@ -81,11 +81,10 @@ __device__ __forceinline__ vw<N> vset(u32 c) {
 // The fused add kernel is bound by the ALU pipe (LOP3/SHF/IADD3: 64 lanes/SM/clk) while the FMA pipe (IMAD,
 // another 64 lanes/SM/clk, co-issued) idles during the hashes. ptxas chooses IADD3 for every addition it sees,
 // so the additions we want on the FMA pipe are written as a*ONE+b with ONE read from constant memory (opaque
-// to the compiler, folded into the IMAD's constant operand, no register), and x>>n as umulhi(x, 2^(32-n)).
+// to the compiler, folded into the IMAD's constant operand, no register).
 // Levels (compile-time, see DESIGN.md K1 "pipe balance"):
 //   ECL_SHA_FMA  0 none | 1 w+K, h+wk | 3 + e', a', S0+maj (ALU 1, FMA 5 adds per round) | 4 all 7 adds
 //   ECL_SHS_FMA  0 none | 1 w[i]+w[i+9] | 2 all three schedule adds
-//   ECL_SHR_FMA  0/1    sigma shifts x>>3, x>>10 as IMAD.HI
 //   ECL_RMD_FMA  0 none | 1 a+(w+K) | 2 + F
 #ifndef ECL_SHA_FMA
 #define ECL_SHA_FMA 4
@@ -93,36 +92,15 @@ __device__ __forceinline__ vw<N> vset(u32 c) {
 #ifndef ECL_SHS_FMA
 #define ECL_SHS_FMA 2
 #endif
-#ifndef ECL_SHR_FMA
-#define ECL_SHR_FMA 0  // IMAD.HI runs at half rate and blocks the ALU pipe too (peak.cuh kinds 7, 10): keep SHF
-#endif
 #ifndef ECL_RMD_FMA
 #define ECL_RMD_FMA 2
 #endif
 static __constant__ u32 ecl_k_one = 1u;
-static __constant__ u32 ecl_k_shr3 = 1u << 29;
-static __constant__ u32 ecl_k_shr10 = 1u << 22;
-// rotations as multiplications: rotr(x, n) = x * 2^(32-n) + (x >> n) = lo + hi of the 64-bit product x * 2^(32-n)
-static __constant__ u32 ecl_k_r7 = 1u << 25, ecl_k_r18 = 1u << 14, ecl_k_r17 = 1u << 15, ecl_k_r19 = 1u << 13;
-static __constant__ u32 ecl_k_l10 = 1u << 10;
-//   ECL_SIG_FMA  0 sigma0/sigma1 rotations as SHF (ALU) | 1 as 64-bit products, halves merged in the XOR (ALU 2,
-//                FMA 3 per sigma) | 2 as product + high half (ALU 1, FMA 5)
-//   ECL_ROTC_FMA 0/1  RIPEMD's c = rotl(c, 10) as IMAD.HI + IMAD (0 ALU, 2 FMA)
-#ifndef ECL_SIG_FMA
-#define ECL_SIG_FMA 0
-#endif
-#ifndef ECL_ROTC_FMA
-#define ECL_ROTC_FMA 0
-#endif
-
+// Measured and dropped (round 1): shifts as IMAD.HI (half rate, peak.cuh kind 7), sigma rotations and RIPEMD's
+// rotl(c, 10) as products (-5 % .. -13 %): rotations and shifts stay on SHF.
 __device__ __forceinline__ u32 fma_add(u32 a, u32 b) {
   u32 d;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(ecl_k_one), "r"(b));
-  return d;
-}
-__device__ __forceinline__ u32 fma_mulhi(u32 a, u32 m) {
-  u32 d;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(m));
   return d;
 }
 template <int N>
@@ -138,67 +116,6 @@ __device__ __forceinline__ vw<N> vfadd(const vw<N> &a, u32 k) {
 #pragma unroll
   for (int i = 0; i < N; ++i) r.l[i] = fma_add(a.l[i], k);
   return r;
-}
-// rotr(x, n) entirely on the FMA pipe; m = 2^(32-n) read from constant memory
-__device__ __forceinline__ u32 fma_rot(u32 x, u32 m) {
-  u32 d;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(m), "r"(fma_mulhi(x, m)));
-  return d;
-}
-// both halves of x * m: lo = x << (32-n), hi = x >> n (one IMAD.WIDE)
-__device__ __forceinline__ void fma_rot_halves(u32 &lo, u32 &hi, u32 x, u32 m) {
-  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(m));
-}
-// sigma(x) = rotr(x, n1) ^ rotr(x, n2) ^ (x >> n3), multipliers m1 = 2^(32-n1), m2 = 2^(32-n2), m3 = 2^(32-n3)
-template <int N>
-__device__ __forceinline__ vw<N> vsigma_fma(const vw<N> &a, u32 m1, u32 m2, u32 m3) {
-  vw<N> r;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-#if ECL_SIG_FMA == 1
-    u32 l1, h1, l2, h2;
-    fma_rot_halves(l1, h1, a.l[i], m1);
-    fma_rot_halves(l2, h2, a.l[i], m2);
-    r.l[i] = (l1 ^ h1 ^ l2) ^ (h2 ^ fma_mulhi(a.l[i], m3));
-#else
-    r.l[i] = fma_rot(a.l[i], m1) ^ fma_rot(a.l[i], m2) ^ fma_mulhi(a.l[i], m3);
-#endif
-  }
-  return r;
-}
-template <int N>
-__device__ __forceinline__ vw<N> vrotl10(const vw<N> &a) {
-#if ECL_ROTC_FMA
-  vw<N> r;
-#pragma unroll
-  for (int i = 0; i < N; ++i) r.l[i] = fma_rot(a.l[i], ecl_k_l10);
-  return r;
-#else
-  return vrotl(a, 10);
-#endif
-}
-
-template <int N>
-__device__ __forceinline__ vw<N> vshr3(const vw<N> &a) {
-#if ECL_SHR_FMA
-  vw<N> r;
-#pragma unroll
-  for (int i = 0; i < N; ++i) r.l[i] = fma_mulhi(a.l[i], ecl_k_shr3);
-  return r;
-#else
-  return vshr(a, 3);
-#endif
-}
-template <int N>
-__device__ __forceinline__ vw<N> vshr10(const vw<N> &a) {
-#if ECL_SHR_FMA
-  vw<N> r;
-#pragma unroll
-  for (int i = 0; i < N; ++i) r.l[i] = fma_mulhi(a.l[i], ecl_k_shr10);
-  return r;
-#else
-  return vshr(a, 10);
-#endif
 }
 
 // ---------------------------------------------------------------- SHA-256 (FIPS 180-4; lib/sha256.c:399-453)
@@ -237,13 +154,8 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
     if (i >= 16) {
       const vw<N> x = w[(i + 1) & 15], y = w[(i + 14) & 15];
       const bool cA = wc[i - 16], cB = wc[i - 15], cC = wc[i - 7], cD = wc[i - 2];
-#if ECL_SIG_FMA
-      const vw<N> s0 = cB ? vrotr(x, 7) ^ vrotr(x, 18) ^ vshr(x, 3) : vsigma_fma(x, ecl_k_r7, ecl_k_r18, ecl_k_shr3);
-      const vw<N> s1 = cD ? vrotr(y, 17) ^ vrotr(y, 19) ^ vshr(y, 10) : vsigma_fma(y, ecl_k_r17, ecl_k_r19, ecl_k_shr10);
-#else
-      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ (cB ? vshr(x, 3) : vshr3(x));
-      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ (cD ? vshr(y, 10) : vshr10(y));
-#endif
+      const vw<N> s0 = vrotr(x, 7) ^ vrotr(x, 18) ^ vshr(x, 3);
+      const vw<N> s1 = vrotr(y, 17) ^ vrotr(y, 19) ^ vshr(y, 10);
 #if ECL_SHS_FMA == 0
       w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
 #else
@@ -305,17 +217,17 @@ __device__ __forceinline__ void sha256_iv(vw<N> st[8]) {
 #if ECL_RMD_FMA == 0
 #define RMD_STEP(F, a, b, c, d, e, wi, k, s)      \
   a = vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e; \
-  c = vrotl10(c);
+  c = vrotl(c, 10);
 #elif ECL_RMD_FMA == 1
 #define RMD_STEP(F, a, b, c, d, e, wi, k, s)                                           \
   a = RMD_CONSTW(wi) ? vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e                    \
                      : vrotl(vfadd(a, RMD_WK(wi, k)) + F(b, c, d), s) + e;             \
-  c = vrotl10(c);
+  c = vrotl(c, 10);
 #else
 #define RMD_STEP(F, a, b, c, d, e, wi, k, s)                                           \
   a = RMD_CONSTW(wi) ? vrotl(a + F(b, c, d) + (w[wi] + (k)), s) + e                    \
                      : vrotl(vfadd(vfadd(a, RMD_WK(wi, k)), F(b, c, d)), s) + e;       \
-  c = vrotl10(c);
+  c = vrotl(c, 10);
 #endif
 
 // digest words of SHA-256 (sha[0..7], big-endian word values) -> h160_t words
