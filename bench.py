@@ -335,6 +335,10 @@ def ours_arm(args):
             if v is not None:
                 line["cpu_baseline"] = {"value": round(v, 3), "unit": "Mkeys/s", "cores": cores, "kind": "reference",
                                         "sample": f"first 2^{n.bit_length() - 1} keys of configs[1], -t {cores}, wall clock ({info.get('binary')}); status: {info.get('status_line')}"}
+                v1, info1 = run_reference_sample(RANGE_S, 1 << 24, 1)  # BASELINE.md §3 asks for -t 1 beside -t nproc
+                if v1 is not None:
+                    line["cpu_baseline"]["single_thread"] = {"value": round(v1, 3), "unit": "Mkeys/s",
+                                                             "sample": f"first 2^24 keys of configs[1], -t 1; status: {info1.get('status_line')}"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "Mkeys/s", "cores": cores, "kind": "reference", "sample": str(info)}
         print(json.dumps(line))
