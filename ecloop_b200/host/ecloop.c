@@ -18,6 +18,7 @@
 #include <locale.h>
 #include <pthread.h>
 #include <signal.h>
+#include <stdatomic.h>
 #include <stdarg.h>
 #include <stdbool.h>
 #include <stdio.h>
@@ -68,7 +69,7 @@ typedef struct app {
   uint64_t t_start, t_update, t_print, t_pause_at, paused_ms;
   volatile bool paused;
   bool finished;
-  int fatal; /* a rank thread hit a library error */
+  atomic_int fatal; /* a rank thread hit a library error (set from any thread, polled without the lock) */
 
   struct mul_pipe *mul; /* mul: stdin reader -> parser threads -> rank threads */
 } app;

@@ -153,7 +153,8 @@ def sparse_filter(H, seed, size_words, fill):
     return H.Filter(bits, None)
 
 
-@pytest.mark.parametrize("seed,flags_name,offs", [(1, "c", 0), (2, "cu", 0), (3, "c_endo", 0), (4, "cu_endo", 5), (5, "u", 13)])
+@pytest.mark.parametrize("seed,flags_name,offs", [(1, "c", 0), (2, "cu", 0), (3, "c_endo", 0), (4, "cu_endo", 5), (5, "u", 13),
+                                                  (6, "cu", 128)])  # 128 = `rnd -d 128:32` (BASELINE configs[4])
 def test_random_spans_vs_oracle(dev, H, E, seed, flags_name, offs):
     flags = {"c": E.A33, "u": E.A65, "cu": E.A33 | E.A65, "c_endo": E.A33 | E.ENDO, "cu_endo": E.A33 | E.A65 | E.ENDO}[flags_name]
     r = random.Random(seed)
