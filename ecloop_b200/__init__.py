@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "ecl_peak_bench_kind",
 )
 PEAK_KINDS = ("lop3", "iadd3", "shf", "imad", "imad_wide", "lop3+imad", "imad_const", "imad_hi", "lop3+imad_const",
-              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf")
+              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad")
 
 
 class EclError(RuntimeError):

@@ -742,7 +742,7 @@ static int run_peak(ecl_dev *dev, double *gops, double *mhz) {
   return ECL_OK;
 }
 
-// one kind of peak.cuh by number (0..15); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
+// one kind of peak.cuh by number (0..18); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
 extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz) {
   if (!dev || !gops) return ECL_E_ARG;
   CK(cudaSetDevice(dev->ordinal));
@@ -765,6 +765,9 @@ extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double 
   case 13: rc = run_peak<13>(dev, gops, &mhz); break;
   case 14: rc = run_peak<14>(dev, gops, &mhz); break;
   case 15: rc = run_peak<15>(dev, gops, &mhz); break;
+  case 16: rc = run_peak<16>(dev, gops, &mhz); break;
+  case 17: rc = run_peak<17>(dev, gops, &mhz); break;
+  case 18: rc = run_peak<18>(dev, gops, &mhz); break;
   default: return fail(dev, ECL_E_ARG, "unknown peak kind %d", kind);
   }
   if (sm_mhz) *sm_mhz = mhz;

@@ -21,6 +21,10 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed,
 #pragma unroll
   for (int c = 0; c < PEAK_CHAINS; ++c) r[c] = seed * (c + 1) + t, q[c] = (uint64_t)r[c] << 7;
   const uint32_t m = seed | 1u, z = seed ^ 0x9e3779b9u;
+  double f[PEAK_CHAINS];  // FP64 chains (kinds 16-18): is the DFMA pipe a third lane beside ALU and FMA?
+#pragma unroll
+  for (int c = 0; c < PEAK_CHAINS; ++c) f[c] = 1.0 + (double)(r[c] & 1023u) * 1e-9;
+  const double fm = 1.0 + (double)(seed & 255u) * 1e-12, fz = (double)(seed & 15u) * 1e-15;
   const long long c0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < PEAK_ITERS; ++it) {
@@ -68,6 +72,15 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed,
           if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
           else asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(r[c]));
         }
+        if (KIND == 16) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f[c]) : "d"(fm), "d"(fz));  // DFMA
+        if (KIND == 17) {  // DFMA + LOP3
+          if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f[c]) : "d"(fm), "d"(fz));
+        }
+        if (KIND == 18) {  // DFMA + IMAD
+          if (c & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[c]) : "r"(m), "r"(z));
+          else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(f[c]) : "d"(fm), "d"(fz));
+        }
         if (KIND == 12) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[c]) : "r"(z));  // 2-input add: IADD3 or IMAD.IADD, ptxas decides
       }
     }
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t seed,
   const long long c1 = clock64();
   uint32_t acc = 0;
 #pragma unroll
-  for (int c = 0; c < PEAK_CHAINS; ++c) acc ^= r[c] ^ (uint32_t)q[c] ^ (uint32_t)(q[c] >> 32);
+  for (int c = 0; c < PEAK_CHAINS; ++c) acc ^= r[c] ^ (uint32_t)q[c] ^ (uint32_t)(q[c] >> 32) ^ (uint32_t)__double2ll_rn(f[c] * 1e6);
   if (acc == 0x12345678u) out[t & 1023] = acc;  // keep the chains alive
   if (t == 0) *cycles = (unsigned long long)(c1 - c0);
 }

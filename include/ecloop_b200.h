@@ -111,7 +111,8 @@ int ecl_prim_bloom(ecl_dev *dev, const uint32_t (*h160)[5], uint8_t *out, uint32
 int ecl_peak_bench(ecl_dev *dev, double out[8]);
 /* one instruction kind / mix of peak.cuh by number: 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 IMAD.WIDE, 5 LOP3+IMAD,
  * 6 IMAD with a constant-bank operand, 7 IMAD.HI, 8 LOP3+IMAD(const), 9 SHF+IMAD.WIDE, 10 LOP3+IMAD.HI,
- * 11 5:3 LOP3:IMAD(const), 12 two-input add, 13 LOP3+IMAD.WIDE, 14 SHF+IMAD, 15 LOP3+SHF. Result in Gops/s (32 lanes x instructions / time). */
+ * 11 5:3 LOP3:IMAD(const), 12 two-input add, 13 LOP3+IMAD.WIDE, 14 SHF+IMAD, 15 LOP3+SHF,
+ * 16 DFMA, 17 DFMA+LOP3, 18 DFMA+IMAD. Result in Gops/s (32 lanes x instructions / time). */
 int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz);
 
 #ifdef __cplusplus
