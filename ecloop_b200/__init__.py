@@ -17,7 +17,7 @@ from . import build as _build
 
 A33, A65, ENDO = 1, 2, 4
 GROUP = 2048
-OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV = range(6)
+OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_MUL_F64, OP_MUL_F64_CHAIN = range(8)
 
 ABI_SYMBOLS = (
     "ecl_abi_version", "ecl_device_count", "ecl_open", "ecl_close", "ecl_last_error", "ecl_set_stream",
@@ -26,7 +26,8 @@ ABI_SYMBOLS = (
     "ecl_peak_bench_kind",
 )
 PEAK_KINDS = ("lop3", "iadd3", "shf", "imad", "imad_wide", "lop3+imad", "imad_const", "imad_hi", "lop3+imad_const",
-              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad")
+              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad",
+              "fe_mul_gmuls", "fe6_mul_f64_gmuls", "fe_mul+384alu_gmuls", "fe6_mul_f64+384alu_gmuls")
 
 
 class EclError(RuntimeError):

@@ -742,7 +742,29 @@ static int run_peak(ecl_dev *dev, double *gops, double *mhz) {
   return ECL_OK;
 }
 
-// one kind of peak.cuh by number (0..18); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
+template <int KIND, int FILL>
+static int run_mulbench(ecl_dev *dev, double *gmuls) {
+  DevBuf<u32> out;
+  CK(out.alloc(1024));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, dev->stream));
+    mulbench_kernel<KIND, FILL><<<dev->sm_count, 512, 0, dev->stream>>>(out.p, 0x9e3779b9u + rep);
+    CK(cudaEventRecord(e1, dev->stream));
+    CK(cudaStreamSynchronize(dev->stream));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  *gmuls = (double)dev->sm_count * 512.0 * MULBENCH_ITERS * 2.0 / (best * 1e-3) / 1e9;
+  return ECL_OK;
+}
+
+// one kind of peak.cuh by number (0..18), or a field-multiplication throughput (19..22, fp64mul.cuh); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
 extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz) {
   if (!dev || !gops) return ECL_E_ARG;
   CK(cudaSetDevice(dev->ordinal));
@@ -768,6 +790,10 @@ extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double 
   case 16: rc = run_peak<16>(dev, gops, &mhz); break;
   case 17: rc = run_peak<17>(dev, gops, &mhz); break;
   case 18: rc = run_peak<18>(dev, gops, &mhz); break;
+  case 19: rc = run_mulbench<0, 0>(dev, gops); break;
+  case 20: rc = run_mulbench<1, 0>(dev, gops); break;
+  case 21: rc = run_mulbench<0, 384>(dev, gops); break;
+  case 22: rc = run_mulbench<1, 384>(dev, gops); break;
   default: return fail(dev, ECL_E_ARG, "unknown peak kind %d", kind);
   }
   if (sm_mhz) *sm_mhz = mhz;

@@ -9,6 +9,7 @@
 #pragma once
 #include "add_kernel.cuh"
 #include "common.cuh"
+#include "fp64mul.cuh"
 
 // ---------------------------------------------------------------- K3: scalar multiples of G
 
@@ -172,6 +173,14 @@ __global__ void prim_fp_kernel(int op, const fe *a, const fe *b, fe *out, u32 n)
   case ECL_OP_ADD: r = fe_add(x, y); break;
   case ECL_OP_SUB: r = fe_sub(x, y); break;
   case ECL_OP_NEG: r = fe_neg(x); break;
+  case ECL_OP_MUL_F64: r = fe6_to_fe(fe6_mul(fe6_from_fe(x), fe6_from_fe(y))); break;
+  case ECL_OP_MUL_F64_CHAIN: {  // x * y^16 without leaving the weak 44-bit-limb form in between
+    fe6 acc = fe6_from_fe(x);
+    const fe6 m = fe6_from_fe(y);
+    for (int i = 0; i < 16; ++i) acc = fe6_mul(acc, m);
+    r = fe6_to_fe(acc);
+    break;
+  }
   default: r = fe_inv(x); break;
   }
   out[i] = r;

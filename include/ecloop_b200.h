@@ -95,7 +95,9 @@ int ecl_set_tuning(ecl_dev *dev, uint32_t groups_per_thread, uint32_t hit_capaci
 
 /* ---- primitive entry points, one per reference routine, used by the parity tests (tests/test_gpu_*.py).
  * All take host pointers and run the same device functions the hot kernels inline. */
-enum { ECL_OP_MUL = 0, ECL_OP_SQR = 1, ECL_OP_ADD = 2, ECL_OP_SUB = 3, ECL_OP_NEG = 4, ECL_OP_INV = 5 };
+enum { ECL_OP_MUL = 0, ECL_OP_SQR = 1, ECL_OP_ADD = 2, ECL_OP_SUB = 3, ECL_OP_NEG = 4, ECL_OP_INV = 5,
+       /* experimental FP64-pipe multiplication (csrc/fp64mul.cuh): a*b, and a*b^16 chained in its own limb form */
+       ECL_OP_MUL_F64 = 6, ECL_OP_MUL_F64_CHAIN = 7 };
 /* fe_modp_mul/sqr/add/sub/neg/inv (lib/ecc.c:269-520) elementwise over n elements */
 int ecl_prim_fp(ecl_dev *dev, int op, const uint64_t (*a)[4], const uint64_t (*b)[4], uint64_t (*out)[4], uint32_t n);
 /* ec_gtable_mul + ec_jacobi_rdc (lib/ecc.c:907-929, 686-693): out_xy[i] = {x[4], y[4]} affine, zeros for k=0 */
@@ -112,7 +114,9 @@ int ecl_peak_bench(ecl_dev *dev, double out[8]);
 /* one instruction kind / mix of peak.cuh by number: 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 IMAD.WIDE, 5 LOP3+IMAD,
  * 6 IMAD with a constant-bank operand, 7 IMAD.HI, 8 LOP3+IMAD(const), 9 SHF+IMAD.WIDE, 10 LOP3+IMAD.HI,
  * 11 5:3 LOP3:IMAD(const), 12 two-input add, 13 LOP3+IMAD.WIDE, 14 SHF+IMAD, 15 LOP3+SHF,
- * 16 DFMA, 17 DFMA+LOP3, 18 DFMA+IMAD. Result in Gops/s (32 lanes x instructions / time). */
+ * 16 DFMA, 17 DFMA+LOP3, 18 DFMA+IMAD. Result in Gops/s (32 lanes x instructions / time).
+ * 19..22: field multiplications per second (G mul/s) of fe_mul (IMAD.WIDE) / fe6_mul (DFMA), alone (19, 20) and with
+ * 384 LOP3/SHF per multiplication beside them (21, 22), 512 threads per SM like the add kernel. */
 int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz);
 
 #ifdef __cplusplus

@@ -43,6 +43,22 @@ def test_fp_mul_sqr(dev):
         assert O.fp_mul(x, y) == x * y % P
 
 
+def test_fp_mul_on_the_fp64_pipe(dev):
+    """experimental fe6_mul (csrc/fp64mul.cuh, 44-bit limbs as doubles, DFMA): same canonical residues as fe_mul for
+    canonical, non-canonical and edge inputs, and 16 chained multiplications in its own weak-limb form"""
+    import ecloop_b200 as E
+
+    r = random.Random(131)
+    ev = edge_values() + [2**256 - 1, P, P + 1, 2**256 - 2**32, 2**44 - 1, 2**44, 2**88 - 1, 2**220, (2**36 - 1) * (2**220)]
+    a = [x for x in ev for _ in ev] + [r.getrandbits(256) for _ in range(6000)]
+    b = [y for _ in ev for y in ev] + [r.getrandbits(256) for _ in range(6000)]
+    got = dev.fp(E.OP_MUL_F64, a, b)
+    assert got == [x * y % P for x, y in zip(a, b)]
+    assert got == dev.fp(E.OP_MUL, a, b)
+    got = dev.fp(E.OP_MUL_F64_CHAIN, a, b)
+    assert got == [x * pow(y, 16, P) % P for x, y in zip(a, b)]
+
+
 def test_fp_mul_accepts_non_canonical_inputs(dev):
     import ecloop_b200 as E
 
