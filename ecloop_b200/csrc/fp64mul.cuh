@@ -153,17 +153,27 @@ __global__ void __launch_bounds__(512, 1) mulbench_kernel(u32 *out, u32 seed) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) f[i] = seed + i * t;
   fe6 d0 = fe6_from_fe(a0), d1 = fe6_from_fe(a1), db = fe6_from_fe(b);
+  // Odd warps start half an iteration late (one filler block first): all warps of an SM run the same deterministic
+  // code, so without this every warp does its multiplications at the same moment and the pipes take turns instead
+  // of overlapping (the two-phase effect DESIGN.md describes for K1).
+  const bool late = FILL > 0 && ((threadIdx.x >> 5) & 1);
 #pragma unroll 1
-  for (int it = 0; it < MULBENCH_ITERS; ++it) {
-    if (KIND == 0) a0 = fe_mul(a0, b), a1 = fe_mul(a1, b);
-    else d0 = fe6_mul(d0, db), d1 = fe6_mul(d1, db);
+  for (int it = 0; it < MULBENCH_ITERS + 1; ++it) {
+    if (it < MULBENCH_ITERS && !(late && it == 0)) {
+      if (KIND == 0) a0 = fe_mul(a0, b), a1 = fe_mul(a1, b);
+      else d0 = fe6_mul(d0, db), d1 = fe6_mul(d1, db);
+    } else if (late && it == MULBENCH_ITERS) {
+      if (KIND == 0) a0 = fe_mul(a0, b), a1 = fe_mul(a1, b);
+      else d0 = fe6_mul(d0, db), d1 = fe6_mul(d1, db);
+    }
+    if (it < MULBENCH_ITERS) {
 #pragma unroll
-    for (int k = 0; k < 2 * FILL / 8; ++k) {
+      for (int k = 0; k < 2 * FILL / 8; ++k) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // not volatile: the compiler is free to interleave these with the multiplication, as in the fused kernel
-        if (k & 1) asm("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(f[i]));
-        else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(f[i]) : "r"(f[(i + 1) & 7]), "r"(seed));
+        for (int i = 0; i < 8; ++i) {
+          if (k & 1) asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(f[i]));
+          else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(f[i]) : "r"(f[(i + 1) & 7]), "r"(seed));
+        }
       }
     }
   }
