@@ -101,3 +101,16 @@ def test_found_line_format():
     h = (0x7025B4EF, 0xB3FF42EB, 0x4D6D71FA, 0xB6B53B4F, 0x4967E3DD)
     assert H.format_found(0, h, 0xC936) == "addr33\t7025b4efb3ff42eb4d6d71fab6b53b4f4967e3dd\t" + "%064x" % 0xC936
     assert H.format_found(1, h, 1, tab=False) == "addr65: 7025b4efb3ff42eb4d6d71fab6b53b4f4967e3dd <- " + "%064x" % 1
+
+
+def test_fp64_multiplication_model_is_exact():
+    """tools/f64mul_model.py: the integer model of csrc/fp64mul.cuh (every intermediate below 2^53, accumulator inside
+    its binade, result congruent to a*b mod p and weak enough to feed the next multiplication)"""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "f64mul_model.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout.startswith("ok")
