@@ -360,3 +360,19 @@ def test_job_plan_rnd_uses_fixed_jobs(hl):
     assert jp.job_keys == 2**21 and sum(n for _, n in spans) == 8 and len(spans) >= 2
     jp, spans = c_job_plan(hl, 0x800000, 0x800000 + 2**20 - 1, 0, fixed=True)  # window smaller than a job: one job
     assert jp.job_keys == 2**21 and spans == [(0x800000, 1)]
+
+
+def test_host_logic_under_asan_ubsan(tmp_path):
+    """the C host's bookkeeping (scalars, filter files, mul feeder, job plan) compiled with -fsanitize=address,undefined
+    and driven by tests/csrc/host_sanitize.c: every check holds and the sanitizers report nothing"""
+    exe = tmp_path / "host_sanitize"
+    srcs = [str(HOST / n) for n in ("u256.c", "filter.c", "sha256_host.c", "mulfeed.c", "jobplan.c")]
+    cmd = ["gcc", "-O1", "-g", "-std=gnu11", "-Wall", "-Wextra", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+           "-I", str(HOST), str(ROOT / "tests" / "csrc" / "host_sanitize.c"), *srcs, "-o", str(exe), "-lm"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in b.stderr and ("cannot find" in b.stderr or "unrecognized" in b.stderr):
+        pytest.skip("no sanitizer runtime in this toolchain")
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe), str(GOLD / "btc-puzzles-hash"), str(tmp_path / "t.blf")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert "ERROR" not in r.stderr and "runtime error" not in r.stderr
