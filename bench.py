@@ -293,7 +293,7 @@ def ours_arm(args):
         pk, pk_src = measured_peaks()
         alu_peak_tops = peaks["lop3_gops"] / 1e3
         achieved_tops = hot_rate * ALU_OPS_PER_KEY / 1e12
-        hbm_achieved = hot_rate * SCRATCH_BYTES_PER_KEY * 2 / 1e9
+        hbm_achieved = hot_rate * SCRATCH_BYTES_PER_KEY / 1e9  # 32 B written + 32 B read per PAIR of keys = 32 B/key
         clocks = sampler.summary()
         per_launch_keys = args.steps * step_keys / max(1, launches // (2 * world))  # launches counts smul + add pairs
         traffic_per_key, traffic_src = measured_traffic()
@@ -321,8 +321,9 @@ def ours_arm(args):
                 "model": f"{ALU_OPS_PER_KEY} canonical ALU-pipe int32 ops per key (SURVEY 8d) x add_kernel keys/s (CUDA events around its launches)",
                 "peak_source": "measured in this process: LOP3.LUT issue rate over all SMs (ecl_peak_bench)",
                 "pipes": {k: round(v, 1) for k, v in peaks.items()},
-                "hbm": {"achieved": round(hbm_achieved, 1), "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                "hbm": {"bound": "hbm", "achieved": round(hbm_achieved, 1), "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                         "frac": round(hbm_achieved / pk.get("hbm_gbs", 6650.0), 4), "peak_source": pk_src,
+                        "traffic": round(traffic_per_key * per_launch_keys) if traffic_per_key else None,
                         "model": "prefix-product scratch: 32 B written + 32 B read per 2 keys"},
             },
             "clocks": clocks,
