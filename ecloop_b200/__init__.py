@@ -17,7 +17,7 @@ from . import build as _build
 
 A33, A65, ENDO = 1, 2, 4
 GROUP = 2048
-OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_MUL_F64, OP_MUL_F64_CHAIN = range(8)
+OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_MUL_F64, OP_MUL_F64_CHAIN, OP_AFFINE_F64_X, OP_AFFINE_F64_Y = range(10)
 
 ABI_SYMBOLS = (
     "ecl_abi_version", "ecl_device_count", "ecl_open", "ecl_close", "ecl_last_error", "ecl_set_stream",

@@ -25,6 +25,13 @@ struct fe6 {
 #define F6_2P44 0x1p44
 #define F6_2M44 0x1p-44
 #define F6_2P52 0x1p52
+// limbs of 1024 p after borrowing 2^46 into each low limb: all >= 2^45 (tools/f64mul_model.py bias_limbs(45))
+#define F6_SUB_BIAS0 83562882710528.0
+#define F6_SUB_BIAS1 87960930222075.0
+#define F6_SUB_BIAS2 87960930222075.0
+#define F6_SUB_BIAS3 87960930222075.0
+#define F6_SUB_BIAS4 87960930222075.0
+#define F6_SUB_BIAS5 70368744177659.0
 
 // 8 x 32-bit words (canonical or not) -> 6 x 44-bit limbs
 __device__ __forceinline__ fe6 fe6_from_fe(const fe &a) {
@@ -83,6 +90,46 @@ __device__ __forceinline__ void f6_split(double &hi, double &lo, double x, doubl
   hi = (t - F6_BIAS) * F6_2M44;
 }
 
+// carries: any limbs below 2^52 -> "normal" limbs (< 2^44 + 64), value preserved mod p (model: carry_norm)
+__device__ __forceinline__ void f6_carry(double c[6]) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double q = __fma_rz(c[k], F6_2M44, F6_2P52) - F6_2P52;
+    c[k] = __fma_rn(q, -F6_2P44, c[k]);
+    c[k + 1] += q;
+  }
+  const double q = __fma_rz(c[5], F6_2M44, F6_2P52) - F6_2P52;
+  c[5] = __fma_rn(q, -F6_2P44, c[5]);
+  c[0] = __fma_rn(q, F6_M, c[0]);
+  const double q0 = __fma_rz(c[0], F6_2M44, F6_2P52) - F6_2P52;
+  c[0] = __fma_rn(q0, -F6_2P44, c[0]);
+  c[1] += q0;
+}
+
+// columns c[0..11] of a product -> normal limbs: fold columns 6..11 with 2^264 = M (mod p), then carries
+__device__ __forceinline__ fe6 f6_fold(double c[12]) {
+  double c6b = 0.0;
+#pragma unroll
+  for (int k = 6; k < 12; ++k) {
+    double h, l;
+    f6_split(h, l, c[k], F6_M);
+    c[k - 6] += l;
+    if (k < 11) c[k - 5] += h;
+    else c6b = h;
+  }
+  {
+    double h, l;
+    f6_split(h, l, c6b, F6_M);
+    c[0] += l, c[1] += h;
+  }
+  f6_carry(c);
+  fe6 r;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r.v[k] = c[k];
+  return r;
+}
+
+// One operand may be "wide" (a raw difference from fe6_sub, limbs < 2^47.3) if the other is normal.
 __device__ __forceinline__ fe6 fe6_mul(const fe6 &a, const fe6 &b) {
   double c[12];
   double hi_prev = 0.0;  // high half of column k-1, already divided by 2^44
@@ -102,40 +149,61 @@ __device__ __forceinline__ fe6 fe6_mul(const fe6 &a, const fe6 &b) {
     hi_prev = (t - F6_BIAS) * F6_2M44;
   }
   c[11] = hi_prev;
-  // fold columns 6..11: c_k * 2^(44 k) = c_k * M * 2^(44 (k - 6))
-  double c6b = 0.0;
+  return f6_fold(c);
+}
+
+// a^2 for a normal a: 21 products, off-diagonal terms once with a doubled operand (model: sqr6)
+__device__ __forceinline__ fe6 fe6_sqr(const fe6 &a) {
+  double a2[6], c[12];
 #pragma unroll
-  for (int k = 6; k < 12; ++k) {
-    double h, l;
-    f6_split(h, l, c[k], F6_M);
-    c[k - 6] += l;
-    if (k < 11) c[k - 5] += h;
-    else c6b = h;
-  }
-  {
-    double h, l;
-    f6_split(h, l, c6b, F6_M);
-    c[0] += l, c[1] += h;
-  }
-  // carries: limbs back below 2^44 (limb 1 may keep a few units more)
+  for (int i = 0; i < 6; ++i) a2[i] = a.v[i] + a.v[i];
+  double hi_prev = 0.0;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const double q = __fma_rz(c[k], F6_2M44, F6_2P52) - F6_2P52;
-    c[k] = __fma_rn(q, -F6_2P44, c[k]);
-    c[k + 1] += q;
+  for (int k = 0; k < 11; ++k) {
+    double t = F6_BIAS, s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int j = k - i;
+      if (j >= 0 && j < 6 && i <= j) {
+        const double x = i == j ? a.v[i] : a2[i];
+        const double tn = __fma_rz(x, a.v[j], t);
+        s += __fma_rn(x, a.v[j], t - tn);
+        t = tn;
+      }
+    }
+    c[k] = s + hi_prev;
+    hi_prev = (t - F6_BIAS) * F6_2M44;
   }
-  {
-    const double q = __fma_rz(c[5], F6_2M44, F6_2P52) - F6_2P52;
-    c[5] = __fma_rn(q, -F6_2P44, c[5]);
-    c[0] = __fma_rn(q, F6_M, c[0]);
-    const double q0 = __fma_rz(c[0], F6_2M44, F6_2P52) - F6_2P52;
-    c[0] = __fma_rn(q0, -F6_2P44, c[0]);
-    c[1] += q0;
-  }
+  c[11] = hi_prev;
+  return f6_fold(c);
+}
+
+// a - b + (a multiple of p whose limbs are all >= 2^45): no negative limb for normal a, b; the result is "wide"
+// (limbs < 2^47.3). The bias is 1024 p (model: bias_limbs(45)).
+__device__ __forceinline__ fe6 fe6_sub(const fe6 &a, const fe6 &b) {
+  const double bias[6] = {F6_SUB_BIAS0, F6_SUB_BIAS1, F6_SUB_BIAS2, F6_SUB_BIAS3, F6_SUB_BIAS4, F6_SUB_BIAS5};
   fe6 r;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) r.v[k] = c[k];
+  for (int i = 0; i < 6; ++i) r.v[i] = (a.v[i] - b.v[i]) + bias[i];
   return r;
+}
+__device__ __forceinline__ fe6 fe6_norm(const fe6 &a) {
+  double c[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) c[i] = a.v[i];
+  f6_carry(c);
+  fe6 r;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r.v[i] = c[i];
+  return r;
+}
+
+// batch_add's body (main.c:378-386) in limb form: P + Q with inv = 1/(qx - px) (model: affine_add6)
+__device__ __forceinline__ void fe6_affine_add(fe6 &rx, fe6 &ry, const fe6 &px, const fe6 &py, const fe6 &qx, const fe6 &qy,
+                                               const fe6 &inv) {
+  const fe6 lam = fe6_mul(fe6_sub(qy, py), inv);
+  rx = fe6_norm(fe6_sub(fe6_sub(fe6_sqr(lam), px), qx));
+  ry = fe6_norm(fe6_sub(fe6_mul(fe6_sub(px, rx), lam), py));
 }
 
 // ---------------------------------------------------------------- throughput of the two multiplications

@@ -181,6 +181,21 @@ __global__ void prim_fp_kernel(int op, const fe *a, const fe *b, fe *out, u32 n)
     r = fe6_to_fe(acc);
     break;
   }
+  case ECL_OP_AFFINE_F64_X:
+  case ECL_OP_AFFINE_F64_Y: {  // (x, y) + G by the affine formula, arithmetic in the FP64 limb form (inverse from fe_inv)
+    fe gx, gy;
+    gx.v[0] = 0x16f81798u, gx.v[1] = 0x59f2815bu, gx.v[2] = 0x2dce28d9u, gx.v[3] = 0x029bfcdbu;
+    gx.v[4] = 0xce870b07u, gx.v[5] = 0x55a06295u, gx.v[6] = 0xf9dcbbacu, gx.v[7] = 0x79be667eu;
+    gy.v[0] = 0xfb10d4b8u, gy.v[1] = 0x9c47d08fu, gy.v[2] = 0xa6855419u, gy.v[3] = 0xfd17b448u;
+    gy.v[4] = 0x0e1108a8u, gy.v[5] = 0x5da4fbfcu, gy.v[6] = 0x26a3c465u, gy.v[7] = 0x483ada77u;
+    fe xc = x, yc = y;
+    fe_canon(xc), fe_canon(yc);
+    const fe inv = fe_inv(fe_sub(gx, xc));
+    fe6 rx, ry;
+    fe6_affine_add(rx, ry, fe6_from_fe(xc), fe6_from_fe(yc), fe6_from_fe(gx), fe6_from_fe(gy), fe6_from_fe(inv));
+    r = fe6_to_fe(op == ECL_OP_AFFINE_F64_X ? rx : ry);
+    break;
+  }
   default: r = fe_inv(x); break;
   }
   out[i] = r;

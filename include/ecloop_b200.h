@@ -97,7 +97,9 @@ int ecl_set_tuning(ecl_dev *dev, uint32_t groups_per_thread, uint32_t hit_capaci
  * All take host pointers and run the same device functions the hot kernels inline. */
 enum { ECL_OP_MUL = 0, ECL_OP_SQR = 1, ECL_OP_ADD = 2, ECL_OP_SUB = 3, ECL_OP_NEG = 4, ECL_OP_INV = 5,
        /* experimental FP64-pipe multiplication (csrc/fp64mul.cuh): a*b, and a*b^16 chained in its own limb form */
-       ECL_OP_MUL_F64 = 6, ECL_OP_MUL_F64_CHAIN = 7 };
+       ECL_OP_MUL_F64 = 6, ECL_OP_MUL_F64_CHAIN = 7,
+       /* x / y of (a, b) + G by batch_add's affine formula (main.c:378-386) computed in that limb form */
+       ECL_OP_AFFINE_F64_X = 8, ECL_OP_AFFINE_F64_Y = 9 };
 /* fe_modp_mul/sqr/add/sub/neg/inv (lib/ecc.c:269-520) elementwise over n elements */
 int ecl_prim_fp(ecl_dev *dev, int op, const uint64_t (*a)[4], const uint64_t (*b)[4], uint64_t (*out)[4], uint32_t n);
 /* ec_gtable_mul + ec_jacobi_rdc (lib/ecc.c:907-929, 686-693): out_xy[i] = {x[4], y[4]} affine, zeros for k=0 */
