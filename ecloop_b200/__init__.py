@@ -17,17 +17,23 @@ from . import build as _build
 
 A33, A65, ENDO = 1, 2, 4
 GROUP = 2048
-OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV, OP_MUL_F64, OP_MUL_F64_CHAIN, OP_AFFINE_F64_X, OP_AFFINE_F64_Y = range(10)
+OP_MUL, OP_SQR, OP_ADD, OP_SUB, OP_NEG, OP_INV = range(6)
+# only libecloop_b200_exp.so (-DECL_EXPERIMENTAL, tests/test_gpu_experimental.py) implements these:
+OP_MUL_F64, OP_MUL_F64_CHAIN, OP_AFFINE_F64_X, OP_AFFINE_F64_Y = range(6, 10)
+MUL_DEPTH = 2
+E_DEGENERATE = -6
 
 ABI_SYMBOLS = (
     "ecl_abi_version", "ecl_device_count", "ecl_open", "ecl_close", "ecl_last_error", "ecl_set_stream",
     "ecl_set_filter", "ecl_set_stride", "ecl_add_submit", "ecl_mul_submit", "ecl_collect", "ecl_last_elapsed_ms",
     "ecl_set_tuning", "ecl_prim_fp", "ecl_prim_scalar_mul", "ecl_prim_hash160", "ecl_prim_bloom", "ecl_peak_bench",
-    "ecl_peak_bench_kind",
+    "ecl_peak_bench_kind", "ecl_filter_alloc", "ecl_filter_write", "ecl_filter_flush", "ecl_filter_commit",
+    "ecl_filter_read", "ecl_filter_copy_peer", "ecl_filter_add", "ecl_filter_generate", "ecl_filter_fill",
+    "ecl_host_alloc", "ecl_host_free",
 )
 PEAK_KINDS = ("lop3", "iadd3", "shf", "imad", "imad_wide", "lop3+imad", "imad_const", "imad_hi", "lop3+imad_const",
-              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad",
-              "fe_mul_gmuls", "fe6_mul_f64_gmuls", "fe_mul+384alu_gmuls", "fe6_mul_f64+384alu_gmuls")
+              "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad")
+PEAK_KINDS_EXPERIMENTAL = ("fe_mul_gmuls", "fe6_mul_f64_gmuls", "fe_mul+384alu_gmuls", "fe6_mul_f64+384alu_gmuls")  # kinds 19..22
 
 
 class EclError(RuntimeError):
@@ -50,23 +56,25 @@ def library_path() -> Path:
     return _build.OUT
 
 
-def load_library(rebuild: bool = False) -> C.CDLL:
-    """Load libecloop_b200.so, building it first if the sources changed. Fails loudly if it cannot be had."""
+def load_library(rebuild: bool = False, experimental: bool = False) -> C.CDLL:
+    """Load libecloop_b200.so, building it first if the sources changed. Fails loudly if it cannot be had.
+    experimental=True loads libecloop_b200_exp.so instead (the same sources with -DECL_EXPERIMENTAL: the FP64-pipe
+    field arithmetic and its microbenchmarks; test-only, never cached as the product library)."""
     global _lib
-    if _lib is not None and not rebuild:
+    if _lib is not None and not rebuild and not experimental:
         return _lib
-    path = _build.OUT
+    path = _build.OUT_EXP if experimental else _build.OUT
     override = os.environ.get("ECLOOP_B200_LIB")  # tuning variants (tools/build_variants.py); never a fallback
-    if override:
+    if override and not experimental:
         path = Path(override)
         if not path.exists():
             raise EclError(-1, f"ECLOOP_B200_LIB={override} does not exist")
     else:
         try:
-            path = _build.build()
+            _build.build()
         except Exception as e:  # no nvcc on this box: use the prebuilt library that travelled with the repo
             if not path.exists():
-                raise EclError(-1, f"libecloop_b200.so is missing and cannot be built here: {e}") from e
+                raise EclError(-1, f"{path.name} is missing and cannot be built here: {e}") from e
     lib = C.CDLL(str(path))
     lib.ecl_last_error.restype = C.c_char_p
     lib.ecl_last_error.argtypes = [C.c_void_p]
@@ -87,7 +95,22 @@ def load_library(rebuild: bool = False) -> C.CDLL:
     lib.ecl_prim_bloom.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.ecl_peak_bench.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.ecl_peak_bench_kind.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    _lib = lib
+    lib.ecl_filter_alloc.argtypes = [C.c_void_p, C.c_uint64]
+    lib.ecl_filter_write.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.ecl_filter_flush.argtypes = [C.c_void_p]
+    lib.ecl_filter_commit.argtypes = [C.c_void_p]
+    lib.ecl_filter_read.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.ecl_filter_copy_peer.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ecl_filter_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.ecl_filter_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_uint64]
+    lib.ecl_filter_fill.argtypes = [C.c_void_p]
+    lib.ecl_filter_fill.restype = C.c_double
+    lib.ecl_host_alloc.argtypes = [C.c_uint64]
+    lib.ecl_host_alloc.restype = C.c_void_p
+    lib.ecl_host_free.argtypes = [C.c_void_p]
+    lib.ecl_host_free.restype = None
+    if not experimental:
+        _lib = lib
     return lib
 
 
@@ -110,8 +133,8 @@ def _ints_from(arr, n, limbs=4):
 class Device:
     """One GPU. Methods map 1:1 onto the C-ABI; see include/ecloop_b200.h for the reference call sites."""
 
-    def __init__(self, ordinal: int = 0):
-        self._lib = load_library()
+    def __init__(self, ordinal: int = 0, experimental: bool = False):
+        self._lib = load_library(experimental=experimental)
         self._h = C.c_void_p()
         rc = self._lib.ecl_open(C.byref(self._h), ordinal)
         if rc != 0:
@@ -154,6 +177,48 @@ class Device:
                 bits = (C.c_uint64 * len(bits))(*bits)
             n = len(bits) if size_words is None else size_words
             self._ck(self._lib.ecl_set_filter(self._h, C.cast(bits, C.c_void_p), n))
+
+    # ---- filters on the device (.blf tooling, lib/utils.c:362-475)
+    def filter_alloc(self, size_words: int):
+        self._ck(self._lib.ecl_filter_alloc(self._h, size_words))
+
+    def filter_write(self, offset_words: int, bits):
+        """bits: numpy uint64 array (any host memory)"""
+        self._ck(self._lib.ecl_filter_write(self._h, offset_words, C.c_void_p(bits.ctypes.data), int(bits.size)))
+        self._ck(self._lib.ecl_filter_flush(self._h))
+
+    def filter_commit(self):
+        self._ck(self._lib.ecl_filter_commit(self._h))
+
+    def filter_read(self, offset_words: int, n_words: int):
+        import numpy as np
+
+        out = np.empty(n_words, dtype=np.uint64)
+        self._ck(self._lib.ecl_filter_read(self._h, offset_words, C.c_void_p(out.ctypes.data), n_words))
+        return out
+
+    def filter_copy_peer(self, src: "Device"):
+        self._ck(self._lib.ecl_filter_copy_peer(self._h, src._h))
+
+    def filter_add(self, h160_words_list) -> int:
+        """blf_gen's insert loop: hashes as 5-tuples of words (or an (n, 5) uint32 numpy array) -> number of new items"""
+        if hasattr(h160_words_list, "ctypes"):
+            n, ptr = int(h160_words_list.shape[0]), C.c_void_p(h160_words_list.ctypes.data)
+            keep = h160_words_list
+        else:
+            n = len(h160_words_list)
+            keep = (C.c_uint32 * (5 * n))(*[w for h in h160_words_list for w in h])
+            ptr = C.cast(keep, C.c_void_p)
+        new = C.c_uint64(0)
+        self._ck(self._lib.ecl_filter_add(self._h, ptr, n, C.byref(new)))
+        del keep
+        return int(new.value)
+
+    def filter_generate(self, size_words: int, fill: float, seed: int):
+        self._ck(self._lib.ecl_filter_generate(self._h, size_words, fill, seed))
+
+    def filter_fill(self) -> float:
+        return float(self._lib.ecl_filter_fill(self._h))
 
     def set_stride(self, stride_k: int):
         self._ck(self._lib.ecl_set_stride(self._h, C.cast(_fe(stride_k), C.c_void_p)))

@@ -1,6 +1,7 @@
 """Build libecloop_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot).
 
-Thirteen translation units compile in parallel: the host API + small kernels, and one fused add-kernel variant per
+Fifteen translation units compile in parallel: the host API + small kernels (twice: product and -DECL_EXPERIMENTAL test
+library), the GPU blf-gen insert (CUB sort), and one fused add-kernel variant per
 address-type / endomorphism combination, each for a filter in shared memory and for a filter in HBM. Objects are cached under build/ keyed by a hash of all sources + flags.
 """
 from __future__ import annotations
@@ -17,6 +18,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OUT = PKG / "libecloop_b200.so"
+OUT_EXP = PKG / "libecloop_b200_exp.so"  # the same library with -DECL_EXPERIMENTAL (FP64-pipe field arithmetic): test-only
 OBJ = ROOT / "build" / "obj"
 ADD_VARIANTS = (1, 2, 3, 5, 6, 7)
 
@@ -46,23 +48,24 @@ def _sources_hash(extra: str = "") -> str:
 def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), variant: str | None = None) -> Path:
     """Compile (if stale) and return the path of libecloop_b200.so. `variant` builds a tuning variant with the
     given -D defines into build/variants/libecloop_b200_<variant>.so (tools/build_variants.py)."""
-    global OUT, OBJ
+    global OUT, OBJ, OUT_EXP
     if variant:
         out, obj = ROOT / "build" / "variants" / f"libecloop_b200_{variant}.so", ROOT / "build" / f"obj_{variant}"
-        saved = (OUT, OBJ)
-        OUT, OBJ = out, obj
+        saved = (OUT, OBJ, OUT_EXP)
+        OUT, OBJ, OUT_EXP = out, obj, out.with_name(out.stem + "_exp.so")
         try:
             out.parent.mkdir(parents=True, exist_ok=True)
             return build(force, verbose, defines)
         finally:
-            OUT, OBJ = saved
+            OUT, OBJ, OUT_EXP = saved
     tag = _sources_hash(" ".join(defines))
     stamp = OBJ / "stamp.txt"
-    if not force and OUT.exists() and stamp.exists() and stamp.read_text() == tag:
+    if not force and OUT.exists() and OUT_EXP.exists() and stamp.exists() and stamp.read_text() == tag:
         return OUT
     nvcc = _nvcc()
     OBJ.mkdir(parents=True, exist_ok=True)
-    jobs = [(CSRC / "ecl_api.cu", OBJ / "ecl_api.o", [])]
+    jobs = [(CSRC / "ecl_api.cu", OBJ / "ecl_api.o", []), (CSRC / "filter_add.cu", OBJ / "filter_add.o", []),
+            (CSRC / "ecl_api.cu", OBJ / "ecl_api_exp.o", ["-DECL_EXPERIMENTAL"])]
     for v in ADD_VARIANTS:
         jobs.append((CSRC / "add_inst.cu", OBJ / f"add_inst_{v}.o", [f"-DADD_VARIANT={v}"]))
         jobs.append((CSRC / "add_inst.cu", OBJ / f"add_inst_hbm_{v}.o", [f"-DADD_VARIANT={v}", "-DADD_HBM=1"]))
@@ -83,10 +86,11 @@ def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] =
     if verbose:
         for (src, obj, extra), log in zip(jobs, logs):
             sys.stderr.write(f"--- {src.name} {extra}\n{log}\n")
-    link = [nvcc, "-shared", "-o", str(OUT), *[str(j[1]) for j in jobs]]
-    r = subprocess.run(link, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for out, skip in ((OUT, "ecl_api_exp.o"), (OUT_EXP, "ecl_api.o")):
+        link = [nvcc, "-shared", "-o", str(out), *[str(j[1]) for j in jobs if j[1].name != skip]]
+        r = subprocess.run(link, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(tag)
     return OUT
 

@@ -5,9 +5,14 @@
 
 #include "add_kernel.cuh"
 
-// the compressed-only, no-endomorphism variant (the headline path) runs the software-pipelined kernel
-#ifndef ECL_ADD_SP
-#define ECL_ADD_SP 1
+// Which instances run the software-pipelined kernel (bit v = ADD_VARIANT v; only variants without the endomorphism
+// exist in that form), and which two-phase instances hash one point at a time (NW = 1: half the loop body).
+// The choice per variant is a measurement (profiles/r02_*_add_variants.txt), not a principle.
+#ifndef ECL_SP_MASK
+#define ECL_SP_MASK 0x2  // variant 1 (addr33)
+#endif
+#ifndef ECL_NW1_MASK
+#define ECL_NW1_MASK 0x0
 #endif
 
 #ifndef ADD_VARIANT
@@ -30,10 +35,12 @@
 #endif
 
 cudaError_t LAUNCH_NAME(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
-#if ECL_ADD_SP && ADD_VARIANT == 1
-  auto fn = add_kernel_sp<ADD_H, ADD_HBM != 0>;
+#if ((ECL_SP_MASK >> ADD_VARIANT) & 1) && !V_ENDO
+  auto fn = add_kernel_sp<ADD_H, V_A33, V_A65, ADD_HBM != 0>;
+#elif (ECL_NW1_MASK >> ADD_VARIANT) & 1
+  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0, 1>;
 #else
-  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0>;
+  auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0, 2>;
 #endif
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

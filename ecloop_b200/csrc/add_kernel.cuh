@@ -6,17 +6,47 @@
 
 struct AddParams {
   const u32 *cx, *cy;  // thread centres, SoA: limb l of thread t at [l*T + t]
-  const uint4 *table;  // H+1 affine points of 64 B: entry i<H = (i+1)*s*G, entry H = 2H*s*G (group step)
+  const uint4 *table;  // H affine points of 64 B: entry i = (i+1)*s*G
+  const uint4 *step_pt;  // the group step 2*Hr*s*G (64 B): an entry of `table` when 2*Hr <= H, else computed per launch
   uint4 *scratch;      // prefix products: element i, half h of thread t at [(2i+h)*T + t]
   BloomView bloom;     // device-global filter
   u32 bloom_smem_words;  // != 0: the filter is staged into shared memory (then == bloom.size)
   HitSink sink;
   u32 T;                  // threads that own work (also the SoA stride)
-  u32 groups_per_thread;  // consecutive groups of 2H keys owned by one thread
-  u64 n_groups;           // groups in this launch
+  u32 groups_per_thread;  // consecutive groups of 2*Hr keys owned by one thread
+  u32 Hr;                 // half group of THIS launch, 2 <= Hr <= H: chosen by the launch planner (ecl_api.cu plan_launch)
+                          // so that T * groups_per_thread * 2*Hr tiles the launch's keys with (almost) no idle lanes
+  u64 n_keys;             // keys of this launch; a key index (relative to the launch) >= n_keys is not reported
   u64 key_off0;           // index (in keys) of the first key of this launch inside the submitted span
+  u32 *err;               // set to 1 when a group's batch product is zero (a centre equal to +-m*s*G: the keys of the
+                          // span reach 0 or n; the reference asserts there, lib/ecc.c:666)
   CandQueue cand;         // HBM kernels only: where stage 1 of the asynchronous probe queues its candidates
 };
+
+// keys of group `g` (0-based inside the launch) of thread t that lie inside the launch: 0 .. 2*Hr
+__device__ __forceinline__ u32 group_keys_inside(const AddParams &p, u64 first_key) {
+  if (first_key >= p.n_keys) return 0u;
+  const u64 left = p.n_keys - first_key;
+  return left < (u64)(2u * p.Hr) ? (u32)left : 2u * p.Hr;
+}
+
+// table (H entries) + the step point behind it, by TMA bulk copies counted on one mbarrier
+#define ADD_STAGE_TABLES(H_)                                                       \
+  extern __shared__ __align__(128) unsigned char smem_raw[];                       \
+  __shared__ __align__(8) u64 mbar;                                                \
+  uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);                                \
+  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw + ((H_) + 1) * 64);               \
+  const u32 tab_bytes = (H_) * 64;                                                 \
+  const u32 bloom_bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;           \
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);                                       \
+  __syncthreads();                                                                 \
+  if (threadIdx.x == 0) {                                                          \
+    mbar_expect_tx(&mbar, tab_bytes + 64u + bloom_bytes);                          \
+    bulk_g2s(tab, p.table, tab_bytes, &mbar);                                      \
+    bulk_g2s(tab + (H_) * 4, p.step_pt, 64u, &mbar);                               \
+    if (bloom_bytes) bulk_g2s(sbloom, p.bloom.bits, bloom_bytes, &mbar);           \
+  }                                                                                \
+  mbar_wait(&mbar, 0);
 
 // The probe pipe of a kernel instance: a ProbePipe in the dynamic shared memory behind the table for HBM filters,
 // an empty tag otherwise. `pipe` is what check_points / probe_hash take.
@@ -46,74 +76,63 @@ __device__ __forceinline__ void pipe_init(ProbePipe<ADD_THREADS> &pp, unsigned c
 __device__ __forceinline__ void pipe_finish(NoPipe &) {}
 __device__ __forceinline__ void pipe_finish(ProbePipe<ADD_THREADS> &pp) { pp.finish(); }
 
-// Thread t owns the consecutive groups [t*c, (t+1)*c) of 2H keys. For one group with centre point
-// P = (start + (g*2H + H)*s)*G it forms every P +- (i+1)*s*G, i < H, sharing ONE field inversion through
+// Thread t owns the consecutive groups [t*c, (t+1)*c) of 2*Hr keys. For one group with centre point
+// P = (start + (g*2Hr + Hr)*s)*G it forms every P +- (i+1)*s*G, i < Hr, sharing ONE field inversion through
 // Montgomery's trick (fe_modp_grpinv, lib/ecc.c:522-540): prefix products go to a coalesced global scratch
-// (32 B per element, written once, read once), the running inverse stays in registers. The group step 2H*s*G
+// (32 B per element, written once, read once), the running inverse stays in registers. The group step 2Hr*s*G
 // rides in the same batch as element 0, so moving to the next group costs one affine addition and no
 // extra inversion (the reference pays a second inversion per group for that, main.c:400).
-// Key order inside a group matches the reference: K-H .. K-1, K, K+1 .. K+H-1 (main.c:363,391).
-template <int H, bool A33, bool A65, bool ENDO, bool HBM>
+// Key order inside a group matches the reference: K-Hr .. K-1, K, K+1 .. K+Hr-1 (main.c:363,391).
+// NW = points hashed side by side at source level (2: both points of a step; 1: one after the other, half the code).
+template <int H, bool A33, bool A65, bool ENDO, bool HBM, int NW = 2>
 __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const AddParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) u64 mbar;
-  uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
-  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw + (H + 1) * 64);
-  const u32 tab_bytes = (H + 1) * 64;
-  const u32 bloom_bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;
-
-  if (threadIdx.x == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&mbar, tab_bytes + bloom_bytes);
-    bulk_g2s(tab, p.table, tab_bytes, &mbar);
-    if (bloom_bytes) bulk_g2s(sbloom, p.bloom.bits, bloom_bytes, &mbar);
-  }
-  mbar_wait(&mbar, 0);
+  static_assert(NW == 1 || NW == 2, "NW is 1 or 2");
+  ADD_STAGE_TABLES(H)
 
   BloomView bv = p.bloom;
   if (p.bloom_smem_words) bv.bits = sbloom;
   PROBE_PIPE_SETUP(HBM, (H + 1) * 64)
 
   // Every thread of the CTA runs the same number of steps so that the CTA can sit behind barriers (lockstep,
-  // see common.cuh): threads without work of their own (past T, or past the last group) run along on the last
+  // see common.cuh): threads without work of their own (past T, or past the last key) run along on the last
   // owner's centre and only their reporting is masked.
   const u32 tid = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 T = p.T;
   const bool owner = tid < T;
   const u32 t = owner ? tid : T - 1;
+  const int Hr = (int)p.Hr;
 
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
 
-  const u64 g0 = (u64)t * p.groups_per_thread;
-  const u64 g1 = g0 + p.groups_per_thread;
   uint4 *scr = p.scratch + tid;  // scratch is sized for whole CTAs
   const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride
 
 #pragma unroll 1
-  for (u64 g = g0; g < g1; ++g) {
-    const bool active = owner && g < p.n_groups;
-    const u64 kc = p.key_off0 + g * (2 * H) + H;  // key index of the centre
+  for (u32 g = 0; g < p.groups_per_thread; ++g) {
+    const u64 first = ((u64)t * p.groups_per_thread + g) * (u64)(2 * Hr);  // first key of the group, launch-relative
+    const u32 inside = owner ? group_keys_inside(p, first) : 0u;           // keys of this group to report
+    const u64 kc = p.key_off0 + first + (u64)Hr;                           // span-relative index of the centre key
 
     // ---- pass 1: prefix products e_0, e_0 e_1, ...   e_0 = step.x - px, e_{i+1} = table[i].x - px
     fe acc = fe_sub(fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]), px);
 #pragma unroll 1
-    for (int i = 0; i < H; ++i) {
+    for (int i = 0; i < Hr; ++i) {
       scr[(size_t)(2 * i) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
       scr[(size_t)(2 * i + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
       const fe d = fe_sub(fe_from_u4(tab[i * 4 + 0], tab[i * 4 + 1]), px);
       acc = fe_mul(acc, d);
     }
-    fe inv = fe_inv(acc);  // 1 / (e_0 ... e_H)
+    if (inside && fe_is_zero(acc)) *p.err = 1u;
+    fe inv = fe_inv(acc);  // 1 / (e_0 ... e_Hr)
 
     // ---- pass 2: peel the inverses off from the far end; two points per step
     // With the filter in HBM thousands of TLB-missing probe fetches are in flight per SM and a scratch load issued
     // behind them takes ~10 us: there the prefix of the NEXT step is fetched before this step's hashes.
-    fe pre_next = fe_from_u4(scr[(size_t)(2 * (H - 1)) * TS], scr[(size_t)(2 * (H - 1) + 1) * TS]);
+    fe pre_next = fe_from_u4(scr[(size_t)(2 * (Hr - 1)) * TS], scr[(size_t)(2 * (Hr - 1) + 1) * TS]);
 #pragma unroll 1
-    for (int i = H - 1; i >= 0; --i) {
+    for (int i = Hr - 1; i >= 0; --i) {
       if (ECL_HASH_SYNC) __syncthreads();
       fe pre;  // e_0 ... e_i
       if (HBM) {
@@ -130,27 +149,43 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
 
       u32 x[2][8], y[2][8];
       u64 off[2];
+      bool act[2];
       fe rx, ry;
-      // lane 0: P - (i+1)sG  -> key K - (i+1)
+      // lane 0: P - (i+1)sG  -> key K - (i+1), index Hr - (i+1) inside the group
       affine_add_inv(rx, ry, px, py, gx, fe_neg(gy), inv_i);
 #pragma unroll
       for (int l = 0; l < 8; ++l) x[0][l] = rx.v[l], y[0][l] = ry.v[l];
       off[0] = kc - (u64)(i + 1);
-      // lane 1: P + (i+1)sG -> key K + (i+1); the far end K+H is outside the group, its slot takes K itself
-      if (i == H - 1) {
+      act[0] = (u32)(Hr - (i + 1)) < inside;
+      // lane 1: P + (i+1)sG -> key K + (i+1); the far end K+Hr is outside the group, its slot takes K itself
+      if (i == Hr - 1) {
         rx = px, ry = py;
         off[1] = kc;
+        act[1] = (u32)Hr < inside;
       } else {
         affine_add_inv(rx, ry, px, py, gx, gy, inv_i);
         off[1] = kc + (u64)(i + 1);
+        act[1] = (u32)(Hr + (i + 1)) < inside;
       }
 #pragma unroll
       for (int l = 0; l < 8; ++l) x[1][l] = rx.v[l], y[1][l] = ry.v[l];
 
-      check_points<2, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x, y, off, active, pipe);
+      if (NW == 2) {
+        check_points<2, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x, y, off, act, pipe);
+      } else {
+#pragma unroll 1
+        for (int n = 0; n < 2; ++n) {
+          u32 x1[1][8], y1[1][8];
+#pragma unroll
+          for (int l = 0; l < 8; ++l) x1[0][l] = n ? x[1][l] : x[0][l], y1[0][l] = n ? y[1][l] : y[0][l];
+          const u64 off1[1] = {n ? off[1] : off[0]};
+          const bool act1[1] = {n ? act[1] : act[0]};
+          check_points<1, A33, A65, ENDO, ECL_HASH_SYNC>(bv, p.sink, x1, y1, off1, act1, pipe);
+        }
+      }
     }
 
-    // ---- next group's centre: P + 2H*s*G with inv = 1/(step.x - px)
+    // ---- next group's centre: P + 2Hr*s*G with inv = 1/(step.x - px)
     {
       const fe sx = fe_from_u4(tab[H * 4 + 0], tab[H * 4 + 1]);
       const fe sy = fe_from_u4(tab[H * 4 + 2], tab[H * 4 + 3]);
@@ -162,47 +197,69 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
   PROBE_PIPE_FINISH(HBM)
 }
 
-// ---------------------------------------------------------------- K1-sp: software-pipelined addr33 variant
-// Same work as add_kernel<H, true, false, false>, restructured so that every basic block of the hot loop holds
-// one hash160 (ALU-pipe: LOP3/SHF/IADD3) AND the field arithmetic that produces the next point (FMA-pipe:
-// IMAD.WIDE): ptxas interleaves the two independent streams, so the two integer pipes work at the same time
-// instead of taking turns (in add_kernel the whole CTA alternates between an FMA-bound field phase and an
+// ---------------------------------------------------------------- K1-sp: the software-pipelined variant (no endomorphism)
+// Same work as add_kernel<H, A33, A65, false>, restructured so that every basic block of the hot loop holds
+// the hash160(s) of one point (ALU-pipe: LOP3/SHF/IADD3) AND the field arithmetic that produces the next point
+// (FMA-pipe: IMAD.WIDE): ptxas interleaves the two independent streams, so the two integer pipes work at the same
+// time instead of taking turns (in add_kernel the whole CTA alternates between an FMA-bound field phase and an
 // ALU-bound hash phase). One pass-2 step = block X: hash(P - (i+1)G) || form P + (i+1)G, then block Y:
 // hash(P + (i+1)G) || peel the inverse of step i-1 and form P - iG.
 
-// hash160 of one compressed point, probe, report; used where nothing is pipelined (once per group)
-static __device__ __noinline__ void check_one_slow(const BloomView &bv, const HitSink &sink, const fe &x, u32 y0, u64 off,
+// hash160(s) of one point, probe, report; used where nothing is pipelined (three times per group)
+template <bool A33, bool A65>
+static __device__ __noinline__ void check_one_slow(const BloomView &bv, const HitSink &sink, const fe &x, const fe &y, u64 off,
                                                    bool active) {
-  u32 xx[1][8], odd[1] = {y0};
+  u32 xx[1][8], yy[1][8];
 #pragma unroll
-  for (int l = 0; l < 8; ++l) xx[0][l] = x.v[l];
+  for (int l = 0; l < 8; ++l) xx[0][l] = x.v[l], yy[0][l] = y.v[l];
   vw<1> h[5];
-  hash160_33<1, 0>(h, xx, odd);
-  const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-  if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, 0, 0);
+  if (A33) {
+    const u32 odd[1] = {y.v[0]};
+    hash160_33<1, 0>(h, xx, odd);
+    const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
+    if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, 0, 0);
+  }
+  if (A65) {
+    hash160_65<1, 0>(h, xx, yy);
+    const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
+    if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, 0, 1);
+  }
+}
+
+// the hash(es) of the point (ax, ay) inside a pipelined block: digest(s) out, probing is done by the caller after the
+// field work of the block so that the probe's branches do not cut the block in two
+template <bool A33, bool A65>
+__device__ __forceinline__ void hash_point(vw<1> (&h33)[5], vw<1> (&h65)[5], const fe &ax, const fe &ay) {
+  u32 xx[1][8], yy[1][8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) xx[0][l] = ax.v[l], yy[0][l] = ay.v[l];
+  if (A33) {
+    const u32 odd[1] = {ay.v[0]};
+    hash160_33<1, 0>(h33, xx, odd);
+  }
+  if (A65) hash160_65<1, 0>(h65, xx, yy);
+}
+template <bool A33, bool A65, class PIPE>
+__device__ __forceinline__ void probe_point(PIPE &pipe, const BloomView &bv, const HitSink &sink, const vw<1> (&h33)[5],
+                                            const vw<1> (&h65)[5], u64 off, bool active) {
+  if (A33) {
+    const u32 hh[5] = {h33[0].l[0], h33[1].l[0], h33[2].l[0], h33[3].l[0], h33[4].l[0]};
+    probe_hash_dyn(pipe, bv, sink, hh, off, 0u, 0u, active);
+  }
+  if (A65) {
+    const u32 hh[5] = {h65[0].l[0], h65[1].l[0], h65[2].l[0], h65[3].l[0], h65[4].l[0]};
+    probe_hash_dyn(pipe, bv, sink, hh, off, 0u, 1u, active);
+  }
 }
 
 // Pass 1 of the NEXT group (its prefix products) rides in block X as well, so after the first group of a launch
 // there is no field-only phase left: the group step is the element peeled FIRST (it is multiplied in last), which
 // makes the next centre known at the start of pass 2, and the prefixes go to the other half of a ping-pong scratch.
-// Elements of a group: f_i = table[i].x - px (i < H), f_H = step.x - px; scratch entry k holds q_k = f_0 ... f_{k-1}.
-template <int H, bool HBM>
+// Elements of a group: f_i = table[i].x - px (i < Hr), f_Hr = step.x - px; scratch entry k holds q_k = f_0 ... f_{k-1}.
+template <int H, bool A33, bool A65, bool HBM>
 __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(const AddParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) u64 mbar;
-  uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
-  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw + (H + 1) * 64);
-  const u32 tab_bytes = (H + 1) * 64;
-  const u32 bloom_bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;
-
-  if (threadIdx.x == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&mbar, tab_bytes + bloom_bytes);
-    bulk_g2s(tab, p.table, tab_bytes, &mbar);
-    if (bloom_bytes) bulk_g2s(sbloom, p.bloom.bits, bloom_bytes, &mbar);
-  }
-  mbar_wait(&mbar, 0);
+  static_assert(H >= 2, "the pipelined loop needs a prologue step and an epilogue step");
+  ADD_STAGE_TABLES(H)
 
   BloomView bv = p.bloom;
   if (p.bloom_smem_words) bv.bits = sbloom;
@@ -212,13 +269,12 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
   const u32 T = p.T;
   const bool owner = tid < T;
   const u32 t = owner ? tid : T - 1;
+  const int Hr = (int)p.Hr;  // >= 2 (plan_launch)
 
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
 
-  const u64 g0 = (u64)t * p.groups_per_thread;
-  const u64 g1 = g0 + p.groups_per_thread;
   const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride (scratch is sized for whole CTAs)
   uint4 *scr_cur = p.scratch + tid;                  // entry k, half h at [(2k + h) * TS]
   uint4 *scr_nxt = scr_cur + (size_t)2 * (H + 1) * TS;
@@ -229,42 +285,44 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
   {
     fe acc = fe_one();
 #pragma unroll 1
-    for (int k = 0; k < H; ++k) {
+    for (int k = 0; k < Hr; ++k) {
       scr_cur[(size_t)(2 * k) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
       scr_cur[(size_t)(2 * k + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
       acc = fe_mul(acc, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), px));
     }
-    scr_cur[(size_t)(2 * H) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
-    scr_cur[(size_t)(2 * H + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+    scr_cur[(size_t)(2 * Hr) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    scr_cur[(size_t)(2 * Hr + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
     tot = fe_mul(acc, fe_sub(sx, px));
   }
 
 #pragma unroll 1
-  for (u64 g = g0; g < g1; ++g) {
-    const bool active = owner && g < p.n_groups;
-    const u64 kc = p.key_off0 + g * (2 * H) + H;
+  for (u32 g = 0; g < p.groups_per_thread; ++g) {
+    const u64 first = ((u64)t * p.groups_per_thread + g) * (u64)(2 * Hr);
+    const u32 inside = owner ? group_keys_inside(p, first) : 0u;
+    const u64 kc = p.key_off0 + first + (u64)Hr;
 
-    fe inv = fe_inv(tot);  // 1 / (f_0 ... f_H)
+    if (inside && fe_is_zero(tot)) *p.err = 1u;
+    fe inv = fe_inv(tot);  // 1 / (f_0 ... f_Hr)
 
-    // ---- the group step first: next centre N = P + 2H*s*G
+    // ---- the group step first: next centre N = P + 2Hr*s*G
     fe nx, ny;
     {
-      const fe qH = fe_from_u4(scr_cur[(size_t)(2 * H) * TS], scr_cur[(size_t)(2 * H + 1) * TS]);
-      const fe inv_s = fe_mul(inv, qH);  // 1 / f_H
-      inv = fe_mul(inv, fe_sub(sx, px));  // 1 / q_H
+      const fe qH = fe_from_u4(scr_cur[(size_t)(2 * Hr) * TS], scr_cur[(size_t)(2 * Hr + 1) * TS]);
+      const fe inv_s = fe_mul(inv, qH);  // 1 / f_Hr
+      inv = fe_mul(inv, fe_sub(sx, px));  // 1 / q_Hr
       const fe sy = fe_from_u4(tab[H * 4 + 2], tab[H * 4 + 3]);
       affine_add_inv(nx, ny, px, py, sx, sy, inv_s);
     }
 
-    // the centre itself (key K) takes the slot of the far end K+H, which lies outside the group
-    check_one_slow(bv, p.sink, px, py.v[0], kc, active);
+    // the centre itself (key K) takes the slot of the far end K+Hr, which lies outside the group
+    check_one_slow<A33, A65>(bv, p.sink, px, py, kc, (u32)Hr < inside);
 
-    // ---- prologue: operands and inverse of step H-1, and its first point P - H*G
-    fe gx = fe_from_u4(tab[(H - 1) * 4 + 0], tab[(H - 1) * 4 + 1]);
-    fe gy = fe_from_u4(tab[(H - 1) * 4 + 2], tab[(H - 1) * 4 + 3]);
+    // ---- prologue: operands and inverse of step Hr-1, and its first point P - Hr*G
+    fe gx = fe_from_u4(tab[(Hr - 1) * 4 + 0], tab[(Hr - 1) * 4 + 1]);
+    fe gy = fe_from_u4(tab[(Hr - 1) * 4 + 2], tab[(Hr - 1) * 4 + 3]);
     fe inv_i;
     {
-      const fe q = fe_from_u4(scr_cur[(size_t)(2 * (H - 1)) * TS], scr_cur[(size_t)(2 * (H - 1) + 1) * TS]);
+      const fe q = fe_from_u4(scr_cur[(size_t)(2 * (Hr - 1)) * TS], scr_cur[(size_t)(2 * (Hr - 1) + 1) * TS]);
       inv_i = fe_mul(inv, q);
       inv = fe_mul(inv, fe_sub(gx, px));
     }
@@ -274,32 +332,22 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
 
     // ---- pass 2, pipelined
 #pragma unroll 1
-    for (int i = H - 1; i >= 1; --i) {
+    for (int i = Hr - 1; i >= 1; --i) {
       if (ECL_HASH_SYNC) __syncthreads();
       // block X: hash P - (i+1)G  ||  form P + (i+1)G, and one pass-1 step of the next group
-      u32 xx[1][8], odd[1];
-      vw<1> h[5];
-#pragma unroll
-      for (int l = 0; l < 8; ++l) xx[0][l] = ax.v[l];
-      odd[0] = ay.v[0];
-      hash160_33<1, 0>(h, xx, odd);
+      vw<1> h33[5], h65[5];
+      hash_point<A33, A65>(h33, h65, ax, ay);
       fe bx, by;
       affine_add_inv(bx, by, px, py, gx, gy, inv_i);
       {
-        const int k = H - 1 - i;
+        const int k = Hr - 1 - i;
         scr_nxt[(size_t)(2 * k) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
         scr_nxt[(size_t)(2 * k + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
         accn = fe_mul(accn, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), nx));
       }
-      {
-        const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        probe_hash_dyn(pipe, bv, p.sink, hh, kc - (u64)(i + 1), 0u, 0u, active);
-      }
+      probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc - (u64)(i + 1), (u32)(Hr - (i + 1)) < inside);
       // block Y: hash P + (i+1)G  ||  peel step i-1 and form P - iG
-#pragma unroll
-      for (int l = 0; l < 8; ++l) xx[0][l] = bx.v[l];
-      odd[0] = by.v[0];
-      hash160_33<1, 0>(h, xx, odd);
+      hash_point<A33, A65>(h33, h65, bx, by);
       {
         const fe q = fe_from_u4(scr_cur[(size_t)(2 * (i - 1)) * TS], scr_cur[(size_t)(2 * (i - 1) + 1) * TS]);
         gx = fe_from_u4(tab[(i - 1) * 4 + 0], tab[(i - 1) * 4 + 1]);
@@ -308,22 +356,20 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
         inv = fe_mul(inv, fe_sub(gx, px));
         affine_add_inv(ax, ay, px, py, gx, fe_neg(gy), inv_i);
       }
-      {
-        const u32 hh[5] = {h[0].l[0], h[1].l[0], h[2].l[0], h[3].l[0], h[4].l[0]};
-        probe_hash_dyn(pipe, bv, p.sink, hh, kc + (u64)(i + 1), 0u, 0u, active && i != H - 1);
-      }
+      // the far end K+Hr (i == Hr-1) lies outside the group: computed along, never reported
+      probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc + (u64)(i + 1), i != Hr - 1 && (u32)(Hr + (i + 1)) < inside);
     }
     // ---- epilogue: step 0 (keys K-1 and K+1), the last two prefixes of the next group
     {
       fe bx, by;
       affine_add_inv(bx, by, px, py, gx, gy, inv_i);
-      check_one_slow(bv, p.sink, ax, ay.v[0], kc - 1, active);
-      check_one_slow(bv, p.sink, bx, by.v[0], kc + 1, active);
-      scr_nxt[(size_t)(2 * (H - 1)) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
-      scr_nxt[(size_t)(2 * (H - 1) + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
-      accn = fe_mul(accn, fe_sub(fe_from_u4(tab[(H - 1) * 4 + 0], tab[(H - 1) * 4 + 1]), nx));
-      scr_nxt[(size_t)(2 * H) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
-      scr_nxt[(size_t)(2 * H + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+      check_one_slow<A33, A65>(bv, p.sink, ax, ay, kc - 1, (u32)(Hr - 1) < inside);
+      check_one_slow<A33, A65>(bv, p.sink, bx, by, kc + 1, (u32)(Hr + 1) < inside);
+      scr_nxt[(size_t)(2 * (Hr - 1)) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+      scr_nxt[(size_t)(2 * (Hr - 1) + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+      accn = fe_mul(accn, fe_sub(fe_from_u4(tab[(Hr - 1) * 4 + 0], tab[(Hr - 1) * 4 + 1]), nx));
+      scr_nxt[(size_t)(2 * Hr) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+      scr_nxt[(size_t)(2 * Hr + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
       tot = fe_mul(accn, fe_sub(sx, nx));
     }
     px = nx, py = ny;
@@ -332,4 +378,3 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
   }
   PROBE_PIPE_FINISH(HBM)
 }
-

@@ -85,7 +85,8 @@ __device__ __forceinline__ fe fe_beta() {
 // check_found_add's inner loop (main.c:291-298) and its endomorphism block (main.c:300-344) for NW points at
 // once. Emission order is restored on the host (ecl_collect sorts), so lanes may report in any order.
 // SYNC: CTA-barrier density inside the hashes (hash160.cuh); only legal when the whole CTA calls this in lockstep.
-// `active` masks the reporting of threads that only run along to keep the CTA in lockstep.
+// `active[n]` masks the reporting of lanes that only run along to keep the CTA in lockstep (threads without work,
+// keys past the end of the launch).
 // PIPE: nullptr_t-like tag type NoPipe (probe inline: filter in shared memory, or a parity kernel) or a ProbePipe
 // (probe_pipe.cuh: filter in HBM, probes in flight while the next hash is computed).
 struct NoPipe {};
@@ -96,10 +97,16 @@ __device__ __forceinline__ void probe_hash(NoPipe &, const BloomView &bv, const 
   if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, endo, kind);
 }
 
+// run-time slot (the pipe counts its submissions): for call sites that are executed for both points of a step
+__device__ __forceinline__ void probe_hash_rt(NoPipe &np, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
+                                              u32 endo, u32 kind, bool active) {
+  probe_hash<0>(np, bv, sink, hh, off, endo, kind, active);
+}
+
 template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0, class PIPE = NoPipe>
-__device__ __forceinline__ void check_points(  // with a ProbePipe NW must be 2: lane n uses slot n
+__device__ __forceinline__ void check_points(  // with a ProbePipe: NW == 2 -> lane n uses slot n; NW == 1 -> run-time slot
     const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
-                                             const u64 (&off)[NW], const bool active, PIPE &pipe) {
+                                             const u64 (&off)[NW], const bool (&active)[NW], PIPE &pipe) {
   constexpr int NE = ENDO ? 6 : 1;
 #pragma unroll 1
   for (int e = 0; e < NE; ++e) {
@@ -130,8 +137,9 @@ __device__ __forceinline__ void check_points(  // with a ProbePipe NW must be 2:
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
-        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active);
+        if (NW == 1) probe_hash_rt(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
+        else if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
+        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
       }
     }
     if (A65) {
@@ -140,8 +148,9 @@ __device__ __forceinline__ void check_points(  // with a ProbePipe NW must be 2:
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
-        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active);
+        if (NW == 1) probe_hash_rt(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
+        else if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
+        else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
       }
     }
   }
@@ -149,7 +158,10 @@ __device__ __forceinline__ void check_points(  // with a ProbePipe NW must be 2:
 
 template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0>
 __device__ __forceinline__ void check_points(const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
-                                             const u64 (&off)[NW], const bool active = true) {
+                                             const u64 (&off)[NW]) {
   NoPipe none;
+  bool active[NW];
+#pragma unroll
+  for (int n = 0; n < NW; ++n) active[n] = true;
   check_points<NW, A33, A65, ENDO, SYNC, NoPipe>(bv, sink, x, y, off, active, none);
 }

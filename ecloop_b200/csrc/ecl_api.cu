@@ -10,36 +10,54 @@
 
 #include <cuda_runtime.h>
 
+#include "filter_kernels.cuh"
 #include "kernels.cuh"
 #include "peak.cuh"
 
-static_assert(ECL_GROUP % (2 * ADD_H) == 0, "a reference group must be a whole number of device groups");
-
 #define GROUP_KEYS (2u * ADD_H)
-#define DEFAULT_GROUPS_PER_THREAD 8u
+#define HR_MIN 64u                        // smallest half group the planner picks (tiny spans still use many threads)
+#define DEFAULT_GROUPS_PER_THREAD 64u     // bounds one launch to Tmax x 64 x 2048 keys (~1.6 s of addr33 work)
 #define DEFAULT_HIT_CAP (1u << 20)
 #define MAX_HITS_PER_KEY 12u  // {33,65} x 6 endomorphism images
+#define SMEM_FILTER_MAX (44u * 1024u)  // filters up to this size ride in shared memory beside the table
 
 typedef unsigned __int128 u128;
 
 // ---------------------------------------------------------------- device object
 
+struct mul_slot {  // one mul submit in flight (ECL_MUL_DEPTH of them)
+  fe *h_keys = nullptr;  // pinned staging copy of the caller's keys
+  fe *d_keys = nullptr;
+  uint4 *d_scratch = nullptr;
+  u32 cap = 0;  // keys the three buffers hold
+  ecl_hit *d_hits = nullptr;
+  u32 *d_hit_count = nullptr;
+  u32 *h_count = nullptr;  // pinned: the hit count comes back with the submit's own stream work
+  u32 n = 0, flags = 0;
+  bool busy = false;
+  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+};
+
 struct ecl_dev {
   int ordinal = 0;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t io_stream = nullptr;  // result downloads of an older mul submit while a younger one computes
   char err[512] = {0};
 
   uint4 *gtab = nullptr;  // window table, GTAB_ENTRIES x 64 B
   u32 *bases = nullptr;
 
-  uint4 *add_table = nullptr;  // (ADD_H+1) x 64 B for the current stride
+  uint4 *add_table = nullptr;  // (ADD_H+1) x 64 B for the current stride: (i+1)*s*G, i < H; entry H = 2H*s*G
+  uint4 *step_buf = nullptr;   // 64 B: the group step of a launch whose Hr has no table entry
   bool table_valid = false;
   u64 stride[4] = {1, 0, 0, 0};
 
   u64 *bloom_bits = nullptr;
   u64 bloom_size = 0, bloom_magic = 0;
-  double bloom_fill = 0.5;  // fraction of set bits (measured by ecl_set_filter for filters that stay in HBM)
+  double bloom_fill = 0.5;  // fraction of set bits (measured for filters that stay in HBM)
+  bool l2_gran_set = false;
+  size_t l2_gran_saved = 0;
 
   u32 Tmax = 0;
   u32 *centres = nullptr;  // 16 x Tmax u32 (SoA x then y)
@@ -47,26 +65,24 @@ struct ecl_dev {
 
   ecl_hit *d_hits = nullptr;
   u32 *d_hit_count = nullptr;
+  u32 *d_err = nullptr;  // degenerate-group flag of the add kernels
   u32 hit_cap = DEFAULT_HIT_CAP;
   u32 groups_per_thread = DEFAULT_GROUPS_PER_THREAD;
 
-  fe *d_scalars = nullptr;
-  u32 scalars_cap = 0;
   // asynchronous probing of filters that do not fit shared memory (probe_pipe.cuh)
   uint4 *cand_entries = nullptr;
-  u32 *cand_counts = nullptr;  // [sm_count] + 1 overflow flag
+  u32 *cand_counts = nullptr;  // [grid_max] counts + 1 overflow flag behind them
+  u32 grid_max = 0;
   u64 cand_cap = 0;            // entries in total
   bool force_inline = false;   // the last span overflowed the queue and is being redone with inline probes
 
-  uint4 *mul_scratch = nullptr;  // 128 B per key of a mul batch (X, Y, Z, prefix product)
-  u32 mul_scratch_cap = 0;
-
-  // pending work (one submit at a time)
+  // pending work: one add submit, or up to ECL_MUL_DEPTH mul submits (collected in submission order)
   int pending = 0;  // 0 none, 1 add, 2 mul
   u64 p_start[4] = {0, 0, 0, 0};
   u64 p_keys = 0;
   u32 p_flags = 0;
-  std::vector<fe> p_scalars;
+  mul_slot mslot[ECL_MUL_DEPTH];
+  u32 m_head = 0, m_count = 0;  // FIFO of busy mul slots: oldest = m_head
   std::vector<ecl_hit> result;  // filled when a collect had to re-run in exact mode
   bool result_ready = false;
 
@@ -91,6 +107,26 @@ static int fail(ecl_dev *d, int code, const char *fmt, ...) {
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
     if (e_ != cudaSuccess) return fail(dev, ECL_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// After a failed submit / collect the handle goes back to "nothing pending" with the stream drained, so that the
+// caller can go on (ECL_E_ARG, ECL_E_OVERFLOW, ECL_E_DEGENERATE) or close the device (ECL_E_CUDA: sticky CUDA errors
+// need a new process). Used on every error exit of the submit / collect functions.
+static int abandon(ecl_dev *dev, int rc) {
+  cudaStreamSynchronize(dev->stream);
+  cudaGetLastError();
+  dev->pending = 0;
+  dev->result_ready = false;
+  dev->force_inline = false;
+  for (auto &s : dev->mslot) s.busy = false;
+  dev->m_head = dev->m_count = 0;
+  return rc;
+}
+#define CKA(call)                                                                                                        \
+  do {                                                                                                                   \
+    cudaError_t e_ = (call);                                                                                             \
+    if (e_ != cudaSuccess)                                                                                               \
+      return abandon(dev, fail(dev, ECL_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
   } while (0)
 
 // ---------------------------------------------------------------- host scalars mod n (bookkeeping only)
@@ -184,16 +220,19 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
     CK(cudaGetDeviceProperties(&prop, ordinal));
     if (prop.major < 10) return fail(dev, ECL_E_NODEV, "device %d is sm_%d%d; this build targets sm_100a only", ordinal, prop.major, prop.minor);
     dev->sm_count = prop.multiProcessorCount;
-    dev->Tmax = (u32)dev->sm_count * ADD_THREADS * ADD_MIN_BLOCKS;
-    // random 8-byte filter probes should cost one 32 B sector of DRAM traffic, not a 128 B line
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    dev->grid_max = (u32)dev->sm_count * ADD_MIN_BLOCKS;
+    dev->Tmax = dev->grid_max * ADD_THREADS;
     CK(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
     dev->stream = dev->own_stream;
+    CK(cudaStreamCreateWithFlags(&dev->io_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&dev->ev_begin));
     CK(cudaEventCreate(&dev->ev_end));
-    CK(cudaMalloc(&dev->d_hit_count, sizeof(u32)));
+    CK(cudaMalloc(&dev->d_hit_count, 2 * sizeof(u32)));
+    dev->d_err = dev->d_hit_count + 1;
+    CK(cudaMemsetAsync(dev->d_hit_count, 0, 2 * sizeof(u32), dev->stream));
     CK(cudaMalloc(&dev->d_hits, (size_t)dev->hit_cap * sizeof(ecl_hit)));
     CK(cudaMalloc(&dev->add_table, (size_t)(ADD_H + 1) * 64));
+    CK(cudaMalloc(&dev->step_buf, 64));
     return build_gtab(dev);
   }();
   if (rc != ECL_OK) {
@@ -205,18 +244,41 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
   return ECL_OK;
 }
 
+static void free_mul_slot(mul_slot &s) {
+  cudaFreeHost(s.h_keys), cudaFreeHost(s.h_count), cudaFree(s.d_keys), cudaFree(s.d_scratch), cudaFree(s.d_hits), cudaFree(s.d_hit_count);
+  for (cudaEvent_t ev : {s.ev_begin, s.ev_k0, s.ev_k1, s.ev_end})
+    if (ev) cudaEventDestroy(ev);
+  s = mul_slot();
+}
+
+// The asynchronous probe wants a random 8-byte filter read to cost one 32 B sector of DRAM traffic, not a 128 B line.
+// The limit is device-wide, so it is only touched while a filter lives in HBM and put back afterwards.
+static void set_l2_granularity(ecl_dev *dev, bool want32) {
+  if (want32 && !dev->l2_gran_set) {
+    if (cudaDeviceGetLimit(&dev->l2_gran_saved, cudaLimitMaxL2FetchGranularity) != cudaSuccess) dev->l2_gran_saved = 64;
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    dev->l2_gran_set = true;
+  } else if (!want32 && dev->l2_gran_set) {
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, dev->l2_gran_saved);
+    dev->l2_gran_set = false;
+  }
+  cudaGetLastError();
+}
+
 extern "C" void ecl_close(ecl_dev *dev) {
   if (!dev) return;
   cudaSetDevice(dev->ordinal);
   cudaDeviceSynchronize();
-  cudaFree(dev->gtab), cudaFree(dev->bases), cudaFree(dev->add_table), cudaFree(dev->bloom_bits);
+  set_l2_granularity(dev, false);
+  cudaFree(dev->gtab), cudaFree(dev->bases), cudaFree(dev->add_table), cudaFree(dev->step_buf), cudaFree(dev->bloom_bits);
   cudaFree(dev->centres), cudaFree(dev->scratch), cudaFree(dev->d_hits), cudaFree(dev->d_hit_count);
-  cudaFree(dev->d_scalars), cudaFree(dev->mul_scratch);
   cudaFree(dev->cand_entries), cudaFree(dev->cand_counts);
+  for (auto &s : dev->mslot) free_mul_slot(s);
   for (auto ev : dev->ev_pool) cudaEventDestroy(ev);
   if (dev->ev_begin) cudaEventDestroy(dev->ev_begin);
   if (dev->ev_end) cudaEventDestroy(dev->ev_end);
   if (dev->own_stream) cudaStreamDestroy(dev->own_stream);
+  if (dev->io_stream) cudaStreamDestroy(dev->io_stream);
   delete dev;
 }
 
@@ -240,6 +302,44 @@ extern "C" int ecl_set_tuning(ecl_dev *dev, uint32_t groups_per_thread, uint32_t
     dev->d_hits = nullptr;
     CK(cudaMalloc(&dev->d_hits, (size_t)cap * sizeof(ecl_hit)));
     dev->hit_cap = cap;
+    for (auto &s : dev->mslot) {  // the mul slots follow on their next use
+      cudaFree(s.d_hits);
+      s.d_hits = nullptr;
+    }
+  }
+  return ECL_OK;
+}
+
+// ---------------------------------------------------------------- filters
+
+static int filter_set_size(ecl_dev *dev, u64 size_words) {
+  CK(cudaFree(dev->bloom_bits));
+  dev->bloom_bits = nullptr, dev->bloom_size = 0;
+  const size_t padded = (size_t)((size_words + 1) / 2 * 2);  // 16-byte multiple for the bulk copy
+  CK(cudaMalloc(&dev->bloom_bits, padded * 8));
+  CK(cudaMemsetAsync(dev->bloom_bits, 0, padded * 8, dev->stream));
+  dev->bloom_size = size_words;
+  dev->bloom_magic = ~0ULL / size_words;
+  dev->bloom_fill = 0.5;
+  return ECL_OK;
+}
+
+static int filter_measure(ecl_dev *dev) {
+  dev->bloom_fill = 0.5;
+  const bool in_hbm = dev->bloom_size * 8 > SMEM_FILTER_MAX;
+  set_l2_granularity(dev, in_hbm);
+  if (in_hbm) {  // stays in HBM: measure its fill for the candidate-queue planner
+    unsigned long long *d_total = nullptr, total = 0;
+    CK(cudaMalloc(&d_total, sizeof total));
+    CK(cudaMemsetAsync(d_total, 0, sizeof total, dev->stream));
+    bloom_popcount_kernel<<<dev->sm_count * 8, 256, 0, dev->stream>>>(dev->bloom_bits, dev->bloom_size, d_total);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, dev->stream));
+    CK(cudaStreamSynchronize(dev->stream));
+    cudaFree(d_total);
+    dev->bloom_fill = (double)total / ((double)dev->bloom_size * 64.0);
+  } else {
+    CK(cudaStreamSynchronize(dev->stream));
   }
   return ECL_OK;
 }
@@ -248,28 +348,99 @@ extern "C" int ecl_set_filter(ecl_dev *dev, const uint64_t *bits, uint64_t size_
   if (!dev || !bits || size_words == 0) return fail(dev, ECL_E_ARG, "ecl_set_filter: empty filter");
   if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_set_filter with work pending");
   CK(cudaSetDevice(dev->ordinal));
-  CK(cudaFree(dev->bloom_bits));
-  dev->bloom_bits = nullptr;
-  const size_t padded = (size_t)((size_words + 1) / 2 * 2);  // 16-byte multiple for the bulk copy
-  CK(cudaMalloc(&dev->bloom_bits, padded * 8));
-  CK(cudaMemsetAsync(dev->bloom_bits, 0, padded * 8, dev->stream));
+  int rc = filter_set_size(dev, size_words);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(dev->bloom_bits, bits, (size_t)size_words * 8, cudaMemcpyHostToDevice, dev->stream));
-  CK(cudaStreamSynchronize(dev->stream));
-  dev->bloom_size = size_words;
-  dev->bloom_magic = ~0ULL / size_words;
-  dev->bloom_fill = 0.5;
-  if (size_words * 8 > 64 * 1024) {  // stays in HBM: measure its fill for the candidate-queue planner
-    unsigned long long *d_total = nullptr, total = 0;
-    CK(cudaMalloc(&d_total, sizeof total));
-    CK(cudaMemsetAsync(d_total, 0, sizeof total, dev->stream));
-    bloom_popcount_kernel<<<dev->sm_count * 8, 256, 0, dev->stream>>>(dev->bloom_bits, size_words, d_total);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, dev->stream));
-    CK(cudaStreamSynchronize(dev->stream));
-    cudaFree(d_total);
-    dev->bloom_fill = (double)total / ((double)size_words * 64.0);
-  }
+  CK(cudaStreamSynchronize(dev->stream));  // `bits` may be pageable and is the caller's again after this call
+  return filter_measure(dev);
+}
+
+extern "C" int ecl_filter_alloc(ecl_dev *dev, uint64_t size_words) {
+  if (!dev || size_words == 0) return fail(dev, ECL_E_ARG, "ecl_filter_alloc: empty filter");
+  if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_filter_alloc with work pending");
+  CK(cudaSetDevice(dev->ordinal));
+  return filter_set_size(dev, size_words);
+}
+
+extern "C" int ecl_filter_write(ecl_dev *dev, uint64_t offset_words, const uint64_t *bits, uint64_t n_words) {
+  if (!dev || !bits) return ECL_E_ARG;
+  if (!dev->bloom_bits || offset_words + n_words > dev->bloom_size || offset_words + n_words < offset_words)
+    return fail(dev, ECL_E_ARG, "ecl_filter_write: words [%llu, +%llu) outside the filter of %llu words", (unsigned long long)offset_words,
+                (unsigned long long)n_words, (unsigned long long)dev->bloom_size);
+  CK(cudaSetDevice(dev->ordinal));
+  CK(cudaMemcpyAsync(dev->bloom_bits + offset_words, bits, (size_t)n_words * 8, cudaMemcpyHostToDevice, dev->stream));
   return ECL_OK;
+}
+
+extern "C" int ecl_filter_flush(ecl_dev *dev) {
+  if (!dev) return ECL_E_ARG;
+  CK(cudaSetDevice(dev->ordinal));
+  CK(cudaStreamSynchronize(dev->stream));
+  return ECL_OK;
+}
+
+extern "C" int ecl_filter_commit(ecl_dev *dev) {
+  if (!dev || !dev->bloom_bits) return fail(dev, ECL_E_ARG, "ecl_filter_commit: no filter");
+  CK(cudaSetDevice(dev->ordinal));
+  return filter_measure(dev);
+}
+
+extern "C" int ecl_filter_read(ecl_dev *dev, uint64_t offset_words, uint64_t *bits, uint64_t n_words) {
+  if (!dev || !bits) return ECL_E_ARG;
+  if (!dev->bloom_bits || offset_words + n_words > dev->bloom_size || offset_words + n_words < offset_words)
+    return fail(dev, ECL_E_ARG, "ecl_filter_read: words outside the filter");
+  CK(cudaSetDevice(dev->ordinal));
+  CK(cudaMemcpyAsync(bits, dev->bloom_bits + offset_words, (size_t)n_words * 8, cudaMemcpyDeviceToHost, dev->stream));
+  CK(cudaStreamSynchronize(dev->stream));
+  return ECL_OK;
+}
+
+extern "C" int ecl_filter_copy_peer(ecl_dev *dev, ecl_dev *src) {
+  if (!dev || !src || !src->bloom_bits) return fail(dev, ECL_E_ARG, "ecl_filter_copy_peer: no source filter");
+  if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_filter_copy_peer with work pending");
+  CK(cudaSetDevice(src->ordinal));
+  CK(cudaStreamSynchronize(src->stream));
+  CK(cudaSetDevice(dev->ordinal));
+  int rc = filter_set_size(dev, src->bloom_size);
+  if (rc) return rc;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, dev->ordinal, src->ordinal) == cudaSuccess && can) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(src->ordinal, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+    cudaGetLastError();
+  }
+  // with peer access this is a direct NVLink copy; without, the runtime stages it through the host
+  CK(cudaMemcpyPeerAsync(dev->bloom_bits, dev->ordinal, src->bloom_bits, src->ordinal, (size_t)src->bloom_size * 8, dev->stream));
+  CK(cudaStreamSynchronize(dev->stream));
+  dev->bloom_fill = src->bloom_fill;
+  set_l2_granularity(dev, dev->bloom_size * 8 > SMEM_FILTER_MAX);
+  return ECL_OK;
+}
+
+extern "C" int ecl_filter_generate(ecl_dev *dev, uint64_t size_words, double fill, uint64_t seed) {
+  if (!dev || size_words == 0 || !(fill >= 0.0 && fill <= 1.0)) return fail(dev, ECL_E_ARG, "ecl_filter_generate: bad arguments");
+  if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_filter_generate with work pending");
+  CK(cudaSetDevice(dev->ordinal));
+  int rc = filter_set_size(dev, size_words);
+  if (rc) return rc;
+  const u32 thr = (u32)(fill * 256.0 + 0.5);
+  filter_generate_kernel<<<dev->sm_count * 8, 256, 0, dev->stream>>>(dev->bloom_bits, size_words, thr, seed);
+  CK(cudaGetLastError());
+  return filter_measure(dev);
+}
+
+extern "C" double ecl_filter_fill(const ecl_dev *dev) { return dev ? dev->bloom_fill : 0.0; }
+
+extern "C" void *ecl_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void ecl_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" int ecl_set_stride(ecl_dev *dev, const uint64_t stride_k[4]) {
@@ -285,6 +456,27 @@ static BloomView bloom_view(const ecl_dev *dev) {
   BloomView b;
   b.bits = dev->bloom_bits, b.size = dev->bloom_size, b.magic = dev->bloom_magic;
   return b;
+}
+
+// blf_gen's insert loop (lib/utils.c:453-465) on the device, exact count included. The final bits do not depend on
+// the order (a skipped hash would have added nothing), the count does: hash i counts iff at least one of its 20 bits
+// is set neither in the filter as it was nor by a hash before i. Per call: (1) blf_has against the filter as it is,
+// and for every hash that fails it the positions of its still-clear bits as sort keys (i rides as the value, pairs
+// are generated in input order); (2) a stable radix sort by position; (3) the head of every run of equal positions
+// is the FIRST hash to set that bit: it counts; (4) all bits are OR-ed in.
+extern "C" int ecl_filter_add(ecl_dev *dev, const uint32_t (*h160)[5], uint32_t n, uint64_t *n_new) {
+  if (!dev || !h160) return ECL_E_ARG;
+  if (!dev->bloom_bits) return fail(dev, ECL_E_ARG, "ecl_filter_add: no filter (ecl_filter_alloc / ecl_set_filter)");
+  if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_filter_add with work pending");
+  if (n_new) *n_new = 0;
+  if (n == 0) return ECL_OK;
+  if (n > (1u << 26)) return fail(dev, ECL_E_ARG, "ecl_filter_add: at most 2^26 hashes per call");
+  CK(cudaSetDevice(dev->ordinal));
+  unsigned long long count = 0;
+  int rc = filter_add_device(dev->stream, bloom_view(dev), dev->bloom_bits, h160, n, &count);
+  if (rc == -1) return fail(dev, ECL_E_CUDA, "ecl_filter_add: %s", cudaGetErrorString(cudaGetLastError()));
+  if (n_new) *n_new = count;
+  return ECL_OK;
 }
 
 // ---------------------------------------------------------------- add path
@@ -308,7 +500,7 @@ static int ensure_add_resources(ecl_dev *dev) {
   return ECL_OK;
 }
 
-// the six add_kernel variants live in add_inst.cu, one translation unit each (parallel build)
+// the add_kernel variants live in add_inst.cu, one translation unit each (parallel build)
 #define DECL_ADD(v) cudaError_t ecl_add_launch_##v(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream);
 DECL_ADD(1) DECL_ADD(2) DECL_ADD(3) DECL_ADD(5) DECL_ADD(6) DECL_ADD(7)
 DECL_ADD(hbm_1) DECL_ADD(hbm_2) DECL_ADD(hbm_3) DECL_ADD(hbm_5) DECL_ADD(hbm_6) DECL_ADD(hbm_7)
@@ -325,12 +517,28 @@ static add_launch_fn pick_add_kernel(u32 flags, bool hbm) {
   }
 }
 
-// The candidate queue of the asynchronous probe: as large as is reasonable (the add kernel wants >= 75 776 threads
-// x 2048 keys per launch and fill^2 of all hashes become candidates), sized once per device.
-static int ensure_cand_queue(ecl_dev *dev) {
-  if (dev->cand_entries) return ECL_OK;
-  u64 want = 1ull << 29;  // 16 GB
+static double cand_per_key(const ecl_dev *dev) {  // expected stage-1 survivors per key, with head-room
+  const u32 hashes_per_key = ((dev->p_flags & ECL_A33) ? 1u : 0u) + ((dev->p_flags & ECL_A65) ? 1u : 0u);
+  const double hashes = (double)hashes_per_key * ((dev->p_flags & ECL_ENDO) ? 6.0 : 1.0);
+  return std::max(1e-6, hashes * dev->bloom_fill * dev->bloom_fill * 1.5);
+}
+
+// The candidate queue of the asynchronous probe, sized for what is asked of it: `want_keys` keys per launch at the
+// measured fill of the current filter and the pending flags (stage 1 passes fill^2 of all hashes), at most 2^29
+// entries (16 GB) and a third of the free memory. It only ever grows.
+static int ensure_cand_queue(ecl_dev *dev, u64 want_keys) {
+  double need = (double)want_keys * cand_per_key(dev);
+  u64 want = 1ull << 16;
+  while (want < (1ull << 29) && (double)want < need) want <<= 1;
   if (const char *env = getenv("ECLOOP_B200_CAND_LOG2")) want = 1ull << std::min(31, std::max(8, atoi(env)));  // test hook
+  if (!dev->cand_counts) {
+    CK(cudaMalloc(&dev->cand_counts, ((size_t)dev->grid_max + 1) * sizeof(u32)));
+    CK(cudaMemsetAsync(dev->cand_counts, 0, ((size_t)dev->grid_max + 1) * sizeof(u32), dev->stream));
+  }
+  if (dev->cand_entries && dev->cand_cap >= want) return ECL_OK;
+  CK(cudaStreamSynchronize(dev->stream));
+  CK(cudaFree(dev->cand_entries));
+  dev->cand_entries = nullptr, dev->cand_cap = 0;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   while (want > 256 && want * 32 > free_b / 3) want >>= 1;
@@ -341,7 +549,6 @@ static int ensure_cand_queue(ecl_dev *dev) {
     if (want <= 256) return fail(dev, ECL_E_CUDA, "cannot allocate the candidate queue");
   }
   dev->cand_cap = want;
-  CK(cudaMalloc(&dev->cand_counts, ((size_t)dev->sm_count + 1) * sizeof(u32)));
   return ECL_OK;
 }
 
@@ -354,62 +561,90 @@ static cudaEvent_t next_event(ecl_dev *dev) {
   return dev->ev_pool[dev->ev_used++];
 }
 
-// Queue the launches covering groups [g_begin, g_end) of the pending span. max_groups_per_launch bounds one launch.
-static int launch_add(ecl_dev *dev, u64 g_begin, u64 g_end, u64 max_groups_per_launch, bool drain_each,
-                      std::vector<ecl_hit> *drain_to) {
+// Launch geometry for `keys` consecutive keys: T threads walk c groups of 2*Hr keys each. The half group Hr is a
+// run-time quantity (table prefix (i+1)*s*G, i < Hr, plus the step 2*Hr*s*G), so instead of rounding the span up to
+// whole rounds of 148 x 512 threads x 2048 keys (a 2^32-key span left 1.2 % of the lanes idle in its tail launch,
+// a 2^29-key span 13 %), Hr is chosen so that T * c * 2*Hr covers the span within one group per thread.
+struct launch_plan {
+  u32 T, c, Hr;
+};
+static launch_plan plan_launch(u64 keys, u32 Tmax) {
+  const u64 full = (u64)Tmax * GROUP_KEYS;
+  const u64 c = (keys + full - 1) / full;
+  const u64 per_thread = (keys + Tmax - 1) / Tmax;
+  u64 Hr = (per_thread + 2 * c - 1) / (2 * c);
+  Hr = std::min<u64>(ADD_H, std::max<u64>(HR_MIN, Hr));
+  launch_plan lp;
+  lp.c = (u32)c, lp.Hr = (u32)Hr;
+  lp.T = (u32)((keys + c * 2 * Hr - 1) / (c * 2 * Hr));
+  return lp;
+}
+
+// Queue the launches covering keys [k_begin, k_end) of the pending span. max_keys_per_launch bounds one launch.
+static int launch_add(ecl_dev *dev, u64 k_begin, u64 k_end, u64 max_keys_per_launch, bool drain_each, std::vector<ecl_hit> *drain_to) {
   const u32 smem_table = (ADD_H + 1) * 64;
   // the filter rides in shared memory when it fits beside the table; otherwise it stays in HBM and is probed
   // asynchronously (probe_pipe.cuh) unless a span is being redone after a candidate-queue overflow, or drained
   // launch by launch for a dense filter (then the inline probe is exact and simple)
   const u64 bloom_bytes = (dev->bloom_size + 1) / 2 * 16;
-  const bool bloom_smem = smem_table + bloom_bytes <= 110u * 1024u;
+  const bool bloom_smem = dev->bloom_size * 8 <= SMEM_FILTER_MAX;
   static const bool no_pipe = getenv("ECLOOP_B200_INLINE_PROBE") != nullptr;  // measurement hook: probe HBM filters inline
   const bool hbm = !bloom_smem && !dev->force_inline && !drain_each && !no_pipe;
   add_launch_fn fn = pick_add_kernel(dev->p_flags, hbm);
   if (!fn) return fail(dev, ECL_E_ARG, "flags select no address type");
   const u32 smem = smem_table + (bloom_smem ? (u32)bloom_bytes : 0u) + (hbm ? ProbePipe<ADD_THREADS>::BYTES : 0u);
+  max_keys_per_launch = std::max<u64>(max_keys_per_launch, GROUP_KEYS);
   if (hbm) {
-    int rc = ensure_cand_queue(dev);
+    int rc = ensure_cand_queue(dev, std::min(k_end - k_begin, max_keys_per_launch));
     if (rc) return rc;
-    // stage 1 passes fill^2 of the hashes: a launch is sized so that the expected candidates use 2/3 of the queue
-    const u32 hashes_per_key = ((dev->p_flags & ECL_A33) ? 1u : 0u) + ((dev->p_flags & ECL_A65) ? 1u : 0u);
-    const double hashes_per_group = (double)GROUP_KEYS * hashes_per_key * ((dev->p_flags & ECL_ENDO) ? 6.0 : 1.0);
-    const double per_group = std::max(1.0, hashes_per_group * dev->bloom_fill * dev->bloom_fill * 1.5);
-    u64 fit = std::max<u64>(1, (u64)((double)dev->cand_cap / per_group));
-    if (fit >= dev->Tmax) fit -= fit % dev->Tmax;  // whole rounds of the grid: every SM keeps its CTA busy
-    max_groups_per_launch = std::min(max_groups_per_launch, fit);
+    // a launch is sized so that the expected candidates use 2/3 of the queue
+    const u64 fit = std::max<u64>(GROUP_KEYS, (u64)((double)dev->cand_cap / cand_per_key(dev)));
+    max_keys_per_launch = std::min(max_keys_per_launch, fit);
   }
+  // equal launches (whole reference groups each) rather than full ones and a remainder
+  if (const char *env = getenv("ECLOOP_B200_MAX_LAUNCH_KEYS"))  // test hook: force several launches for a small span
+    max_keys_per_launch = std::max<u64>(GROUP_KEYS, strtoull(env, nullptr, 10) / GROUP_KEYS * GROUP_KEYS);
+  const u64 span = k_end - k_begin;
+  const u64 n_launches = (span + max_keys_per_launch - 1) / max_keys_per_launch;
+  const u64 per_launch = ((span + n_launches - 1) / n_launches + GROUP_KEYS - 1) / GROUP_KEYS * GROUP_KEYS;
 
-  u64 g = g_begin;
-  while (g < g_end) {
-    const u64 L = std::min<u64>(g_end - g, max_groups_per_launch);
-    const u64 c = (L + dev->Tmax - 1) / dev->Tmax;  // groups per thread
-    const u32 T = (u32)((L + c - 1) / c);
-    // centres: (start + (g*2H + H + t*c*2H) * stride) * G   (GStart, main.c:359-360)
-    u64 k0[4], step[4];
+  u64 k = k_begin;
+  while (k < k_end) {
+    const u64 L = std::min<u64>(k_end - k, per_launch);
+    const launch_plan lp = plan_launch(L, dev->Tmax);
+    // centres: (start + (k + Hr + t*c*2Hr) * stride) * G   (GStart, main.c:359-360)
+    u64 k0[4], step[4], kstep[4];
     const u64 zero[4] = {0, 0, 0, 0};
-    sc_muladd64(k0, dev->stride, g * GROUP_KEYS + ADD_H, dev->p_start);
-    sc_muladd64(step, dev->stride, c * GROUP_KEYS, zero);
+    sc_muladd64(k0, dev->stride, k + lp.Hr, dev->p_start);
+    sc_muladd64(step, dev->stride, (u64)lp.c * 2 * lp.Hr, zero);
     SmulParams sp;
     memset(&sp, 0, sizeof sp);
-    sp.k0 = to_fe(k0), sp.step = to_fe(step), sp.gtab = dev->gtab, sp.count = T, sp.mode = 1, sp.out = dev->centres;
-    smul_kernel<<<(T + 127) / 128, 128, 0, dev->stream>>>(sp);
+    sp.k0 = to_fe(k0), sp.step = to_fe(step), sp.gtab = dev->gtab, sp.count = lp.T, sp.mode = 1, sp.out = dev->centres;
+    const uint4 *step_pt;
+    if (lp.Hr == ADD_H) step_pt = dev->add_table + (size_t)ADD_H * 4;
+    else if (2 * lp.Hr <= ADD_H) step_pt = dev->add_table + (size_t)(2 * lp.Hr - 1) * 4;
+    else {  // 2*Hr*s*G is not in the table: one more thread of the centre kernel computes it
+      sc_muladd64(kstep, dev->stride, 2 * (u64)lp.Hr, zero);
+      sp.extra_k = to_fe(kstep), sp.extra_out = (u32 *)dev->step_buf;
+      step_pt = dev->step_buf;
+    }
+    smul_kernel<<<(lp.T + 1 + 127) / 128, 128, 0, dev->stream>>>(sp);
     CK(cudaGetLastError());
 
     AddParams ap;
     memset(&ap, 0, sizeof ap);
-    ap.cx = dev->centres, ap.cy = dev->centres + (size_t)8 * T;
-    ap.table = dev->add_table, ap.scratch = dev->scratch;
+    ap.cx = dev->centres, ap.cy = dev->centres + (size_t)8 * lp.T;
+    ap.table = dev->add_table, ap.step_pt = step_pt, ap.scratch = dev->scratch;
     ap.bloom = bloom_view(dev);
     ap.bloom_smem_words = bloom_smem ? (u32)dev->bloom_size : 0u;
     ap.sink.hits = dev->d_hits, ap.sink.count = dev->d_hit_count, ap.sink.cap = dev->hit_cap;
-    ap.T = T, ap.groups_per_thread = (u32)c, ap.n_groups = L, ap.key_off0 = g * GROUP_KEYS;
-    const u32 grid = (T + ADD_THREADS - 1) / ADD_THREADS;
+    ap.T = lp.T, ap.groups_per_thread = lp.c, ap.Hr = lp.Hr, ap.n_keys = L, ap.key_off0 = k, ap.err = dev->d_err;
+    const u32 grid = (lp.T + ADD_THREADS - 1) / ADD_THREADS;
     if (hbm) {
       ap.cand.entries = dev->cand_entries, ap.cand.counts = dev->cand_counts;
-      ap.cand.overflow = dev->cand_counts + dev->sm_count;
+      ap.cand.overflow = dev->cand_counts + dev->grid_max;
       ap.cand.cap_per_cta = (u32)std::min<u64>(dev->cand_cap / grid, 0xffffffffu);
-      CK(cudaMemsetAsync(dev->cand_counts, 0, (size_t)dev->sm_count * sizeof(u32), dev->stream));  // not the flag
+      CK(cudaMemsetAsync(dev->cand_counts, 0, (size_t)dev->grid_max * sizeof(u32), dev->stream));  // not the flag
     }
     cudaEvent_t e0 = next_event(dev), e1 = next_event(dev);
     if (!e0 || !e1) return fail(dev, ECL_E_CUDA, "cudaEventCreate failed");
@@ -422,16 +657,20 @@ static int launch_add(ecl_dev *dev, u64 g_begin, u64 g_end, u64 max_groups_per_l
     }
     CK(cudaEventRecord(e1, dev->stream));
     dev->launches += 2;
-    g += L;
+    k += L;
 
     if (drain_each) {
       CK(cudaStreamSynchronize(dev->stream));
       u32 cnt = 0;
-      CK(cudaMemcpy(&cnt, dev->d_hit_count, sizeof cnt, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(&cnt, dev->d_hit_count, sizeof cnt, cudaMemcpyDeviceToHost, dev->stream));
+      CK(cudaStreamSynchronize(dev->stream));
       if (cnt > dev->hit_cap) return fail(dev, ECL_E_OVERFLOW, "hit buffer overflow in exact mode (%u > %u)", cnt, dev->hit_cap);
       const size_t old = drain_to->size();
       drain_to->resize(old + cnt);
-      if (cnt) CK(cudaMemcpy(drain_to->data() + old, dev->d_hits, (size_t)cnt * sizeof(ecl_hit), cudaMemcpyDeviceToHost));
+      if (cnt) {
+        CK(cudaMemcpyAsync(drain_to->data() + old, dev->d_hits, (size_t)cnt * sizeof(ecl_hit), cudaMemcpyDeviceToHost, dev->stream));
+        CK(cudaStreamSynchronize(dev->stream));
+      }
       CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
     }
   }
@@ -444,88 +683,126 @@ extern "C" int ecl_add_submit(ecl_dev *dev, const uint64_t start_pk[4], uint64_t
   if (!dev->bloom_bits) return fail(dev, ECL_E_ARG, "no filter set (ecl_set_filter)");
   if (n_keys == 0 || n_keys % ECL_GROUP) return fail(dev, ECL_E_ARG, "n_keys %llu is not a positive multiple of %u", (unsigned long long)n_keys, ECL_GROUP);
   if (!(flags & (ECL_A33 | ECL_A65))) return fail(dev, ECL_E_ARG, "flags select no address type");
-  CK(cudaSetDevice(dev->ordinal));
+  CKA(cudaSetDevice(dev->ordinal));
   dev->ev_used = 0, dev->launches = 0;
   dev->result.clear(), dev->result_ready = false;
-  CK(cudaEventRecord(dev->ev_begin, dev->stream));
+  CKA(cudaEventRecord(dev->ev_begin, dev->stream));
   int rc = ensure_add_resources(dev);
-  if (rc) return rc;
+  if (rc) return abandon(dev, rc);
   memcpy(dev->p_start, start_pk, 32);
   dev->p_keys = n_keys, dev->p_flags = flags;
-  CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
+  CKA(cudaMemsetAsync(dev->d_hit_count, 0, 2 * sizeof(u32), dev->stream));  // hit cursor + degenerate-group flag
   dev->force_inline = false;
-  if (dev->cand_counts) CK(cudaMemsetAsync(dev->cand_counts + dev->sm_count, 0, sizeof(u32), dev->stream));
-  const u64 n_groups = n_keys / GROUP_KEYS;
-  rc = launch_add(dev, 0, n_groups, (u64)dev->Tmax * dev->groups_per_thread, false, nullptr);
-  if (rc) return rc;
-  CK(cudaEventRecord(dev->ev_end, dev->stream));
+  if (dev->cand_counts) CKA(cudaMemsetAsync(dev->cand_counts + dev->grid_max, 0, sizeof(u32), dev->stream));
+  rc = launch_add(dev, 0, n_keys, (u64)dev->Tmax * dev->groups_per_thread * GROUP_KEYS, false, nullptr);
+  if (rc) return abandon(dev, rc);
+  CKA(cudaEventRecord(dev->ev_end, dev->stream));
   dev->pending = 1;
   return ECL_OK;
 }
 
 // ---------------------------------------------------------------- mul path
 
-typedef void (*mul_kernel_fn)(const MulParams);
-static mul_kernel_fn pick_mul_kernel(u32 flags) {
+typedef void (*mul_hash_fn)(const MulHashParams);
+#ifndef ECL_MUL_NW
+#define ECL_MUL_NW 2
+#endif
+static mul_hash_fn pick_mul_hash(u32 flags) {
   const bool c = flags & ECL_A33, u = flags & ECL_A65;
-  if (c && u) return mul_kernel<true, true>;
-  if (c) return mul_kernel<true, false>;
-  if (u) return mul_kernel<false, true>;
+  if (c && u) return mul_hash_kernel<true, true, ECL_MUL_NW>;
+  if (c) return mul_hash_kernel<true, false, ECL_MUL_NW>;
+  if (u) return mul_hash_kernel<false, true, ECL_MUL_NW>;
   return nullptr;
 }
 
-static int launch_mul(ecl_dev *dev, u32 begin, u32 end) {
-  MulParams mp;
-  memset(&mp, 0, sizeof mp);
-  mp.scalars = dev->d_scalars + begin, mp.gtab = dev->gtab, mp.bloom = bloom_view(dev);
-  mp.sink.hits = dev->d_hits, mp.sink.count = dev->d_hit_count, mp.sink.cap = dev->hit_cap;
-  mp.count = end - begin;
-  // keys per thread: as many as it takes to keep ~768 threads per SM busy, so that small batches still spread
-  // over the whole GPU and large ones amortise the per-thread inversion
-  const u32 want_threads = (u32)dev->sm_count * 768u;
-  mp.B = std::min<u32>(64u, (mp.count + want_threads - 1) / want_threads);
-  if (mp.B == 0) mp.B = 1;
-  mp.T = (mp.count + mp.B - 1) / mp.B;
-  if (mp.count > dev->mul_scratch_cap) {
-    CK(cudaFree(dev->mul_scratch));
-    dev->mul_scratch = nullptr, dev->mul_scratch_cap = 0;
-    CK(cudaMalloc(&dev->mul_scratch, ((size_t)mp.count + 64) * 128));
-    dev->mul_scratch_cap = mp.count;
+static int ensure_mul_slot(ecl_dev *dev, mul_slot &s, u32 n) {
+  if (!s.ev_begin) {
+    CK(cudaEventCreate(&s.ev_begin));
+    CK(cudaEventCreate(&s.ev_k0));
+    CK(cudaEventCreate(&s.ev_k1));
+    CK(cudaEventCreate(&s.ev_end));
+    CK(cudaMalloc(&s.d_hit_count, sizeof(u32)));
+    CK(cudaMallocHost(&s.h_count, sizeof(u32)));
   }
-  mp.scratch = dev->mul_scratch;
-  cudaEvent_t e0 = next_event(dev), e1 = next_event(dev);
-  if (!e0 || !e1) return fail(dev, ECL_E_CUDA, "cudaEventCreate failed");
-  CK(cudaEventRecord(e0, dev->stream));
-  pick_mul_kernel(dev->p_flags)<<<(mp.T + 127) / 128, 128, 0, dev->stream>>>(mp);
+  if (!s.d_hits) CK(cudaMalloc(&s.d_hits, (size_t)dev->hit_cap * sizeof(ecl_hit)));
+  if (n > s.cap) {
+    const u32 cap = std::max<u32>(n, 1u << 16);
+    cudaFreeHost(s.h_keys), cudaFree(s.d_keys), cudaFree(s.d_scratch);
+    s.h_keys = nullptr, s.d_keys = nullptr, s.d_scratch = nullptr, s.cap = 0;
+    CK(cudaMallocHost(&s.h_keys, (size_t)cap * sizeof(fe)));
+    CK(cudaMalloc(&s.d_keys, (size_t)cap * sizeof(fe)));
+    CK(cudaMalloc(&s.d_scratch, ((size_t)cap + 64) * 128));
+    s.cap = cap;
+  }
+  return ECL_OK;
+}
+
+// geometry of K2a for n keys: thread t owns keys m*T + t, m < B
+static void mul_geometry(const ecl_dev *dev, u32 n, u32 *T, u32 *B) {
+  // keys per thread: as many as it takes to keep ~1024 threads per SM busy, so that small batches still spread
+  // over the whole GPU and large ones amortise the per-thread inversion (270 multiplications)
+  const u32 want_threads = (u32)dev->sm_count * 1024u;
+  u32 b = std::min<u32>(64u, (n + want_threads - 1) / want_threads);
+  if (b == 0) b = 1;
+  *B = b, *T = (n + b - 1) / b;
+}
+
+// K2b over keys [begin, end) of a slot whose points are already affine
+static int launch_mul_hash(ecl_dev *dev, mul_slot &s, u32 begin, u32 end) {
+  u32 T, B;
+  mul_geometry(dev, s.n, &T, &B);
+  MulHashParams hp;
+  memset(&hp, 0, sizeof hp);
+  hp.scratch = s.d_scratch, hp.bloom = bloom_view(dev);
+  const bool bloom_smem = dev->bloom_size * 8 <= SMEM_FILTER_MAX;
+  hp.bloom_smem_words = bloom_smem ? (u32)dev->bloom_size : 0u;
+  hp.sink.hits = s.d_hits, hp.sink.count = s.d_hit_count, hp.sink.cap = dev->hit_cap;
+  hp.T = T, hp.begin = begin, hp.end = end;
+  const u32 per_cta = 512u * ECL_MUL_NW;
+  const u32 grid = std::max<u32>(1u, std::min<u32>((u32)dev->sm_count, (end - begin + per_cta - 1) / per_cta));
+  const u32 smem = bloom_smem ? (u32)((dev->bloom_size + 1) / 2 * 16) : 0u;
+  mul_hash_fn fn = pick_mul_hash(s.flags);
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<grid, 512, smem, dev->stream>>>(hp);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e1, dev->stream));
   dev->launches++;
   return ECL_OK;
 }
 
 extern "C" int ecl_mul_submit(ecl_dev *dev, const uint64_t (*pks)[4], uint32_t n, uint32_t flags) {
   if (!dev || !pks || n == 0) return fail(dev, ECL_E_ARG, "ecl_mul_submit: no keys");
-  if (dev->pending) return fail(dev, ECL_E_STATE, "a submit is already pending; call ecl_collect first");
+  if (dev->pending == 1) return fail(dev, ECL_E_STATE, "an add submit is pending; call ecl_collect first");
+  if (dev->m_count == ECL_MUL_DEPTH) return fail(dev, ECL_E_STATE, "%d mul submits are already pending; call ecl_collect first", ECL_MUL_DEPTH);
   if (!dev->bloom_bits) return fail(dev, ECL_E_ARG, "no filter set (ecl_set_filter)");
-  if (!pick_mul_kernel(flags)) return fail(dev, ECL_E_ARG, "flags select no address type");
-  CK(cudaSetDevice(dev->ordinal));
-  dev->ev_used = 0, dev->launches = 0;
-  dev->result.clear(), dev->result_ready = false;
-  if (n > dev->scalars_cap) {
-    CK(cudaFree(dev->d_scalars));
-    dev->d_scalars = nullptr;
-    CK(cudaMalloc(&dev->d_scalars, (size_t)n * sizeof(fe)));
-    dev->scalars_cap = n;
-  }
-  CK(cudaEventRecord(dev->ev_begin, dev->stream));
-  CK(cudaMemcpyAsync(dev->d_scalars, pks, (size_t)n * 32, cudaMemcpyHostToDevice, dev->stream));
-  CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
-  dev->p_keys = n, dev->p_flags = flags;
+  if (!pick_mul_hash(flags)) return fail(dev, ECL_E_ARG, "flags select no address type");
+  CKA(cudaSetDevice(dev->ordinal));
+  mul_slot &s = dev->mslot[(dev->m_head + dev->m_count) % ECL_MUL_DEPTH];
+  int rc = ensure_mul_slot(dev, s, n);
+  if (rc) return abandon(dev, rc);
   // the (hi, lo) limb image of uint64_t[4] equals fe's 8 x u32 on a little-endian host
-  int rc = launch_mul(dev, 0, n);
-  if (rc) return rc;
-  CK(cudaEventRecord(dev->ev_end, dev->stream));
+  memcpy(s.h_keys, pks, (size_t)n * 32);
+  s.n = n, s.flags = flags;
+  CKA(cudaEventRecord(s.ev_begin, dev->stream));
+  CKA(cudaMemcpyAsync(s.d_keys, s.h_keys, (size_t)n * 32, cudaMemcpyHostToDevice, dev->stream));
+  CKA(cudaMemsetAsync(s.d_hit_count, 0, sizeof(u32), dev->stream));
+  MulParams mp;
+  memset(&mp, 0, sizeof mp);
+  mp.scalars = s.d_keys, mp.gtab = dev->gtab, mp.scratch = s.d_scratch, mp.count = n;
+  mul_geometry(dev, n, &mp.T, &mp.B);
+  dev->launches = 0;
+  CKA(cudaEventRecord(s.ev_k0, dev->stream));
+  mul_points_kernel<<<(mp.T + 255) / 256, 256, 0, dev->stream>>>(mp);
+  CKA(cudaGetLastError());
+  dev->launches++;
+  rc = launch_mul_hash(dev, s, 0, n);
+  if (rc) return abandon(dev, rc);
+  CKA(cudaEventRecord(s.ev_k1, dev->stream));
+  CKA(cudaMemcpyAsync(s.h_count, s.d_hit_count, sizeof(u32), cudaMemcpyDeviceToHost, dev->stream));
+  CKA(cudaEventRecord(s.ev_end, dev->stream));
+  s.busy = true;
+  dev->m_count++;
   dev->pending = 2;
+  dev->result.clear(), dev->result_ready = false;
   return ECL_OK;
 }
 
@@ -545,80 +822,117 @@ static bool hit_less_mul(const ecl_hit &a, const ecl_hit &b) {
   return a.kind < b.kind;
 }
 
+// blocking copy of a device word / buffer on the device's stream (the stream is non-blocking: the legacy default
+// stream does not order with it)
+static cudaError_t fetch(ecl_dev *dev, void *dst, const void *src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(dev->stream);
+}
+
+static int collect_add(ecl_dev *dev) {
+  CKA(cudaStreamSynchronize(dev->stream));
+  float ms = 0;
+  CKA(cudaEventElapsedTime(&ms, dev->ev_begin, dev->ev_end));
+  dev->last_total_ms = ms;
+  dev->last_hot_ms = 0;
+  for (size_t i = 0; i + 1 < dev->ev_used; i += 2) {
+    CKA(cudaEventElapsedTime(&ms, dev->ev_pool[i], dev->ev_pool[i + 1]));
+    dev->last_hot_ms += ms;
+  }
+  dev->last_launches = dev->launches;
+  u32 head[2] = {0, 0};  // hit cursor, degenerate flag
+  CKA(fetch(dev, head, dev->d_hit_count, sizeof head));
+  if (head[1])
+    return abandon(dev, fail(dev, ECL_E_DEGENERATE, "the span reaches key 0 or n (a group centre equals +-m*stride*G): no inverse there; "
+                                                     "the reference asserts at this point (lib/ecc.c:666)"));
+  if (dev->cand_counts && !dev->force_inline) {
+    // the asynchronous probe's candidate queue overflowed (a filter far denser than a bloom filter should be):
+    // nothing may be lost, so the span is redone with the probes inline
+    u32 ovf = 0;
+    CKA(fetch(dev, &ovf, dev->cand_counts + dev->grid_max, sizeof ovf));
+    if (ovf) {
+      dev->force_inline = true;
+      CKA(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
+      CKA(cudaMemsetAsync(dev->cand_counts + dev->grid_max, 0, sizeof(u32), dev->stream));
+      int rc2 = launch_add(dev, 0, dev->p_keys, (u64)dev->Tmax * dev->groups_per_thread * GROUP_KEYS, false, nullptr);
+      if (rc2) return abandon(dev, rc2);
+      CKA(fetch(dev, head, dev->d_hit_count, sizeof head));
+    }
+  }
+  const u32 cnt = head[0];
+  dev->result.clear();
+  if (cnt <= dev->hit_cap) {
+    dev->result.resize(cnt);
+    if (cnt) CKA(fetch(dev, dev->result.data(), dev->d_hits, (size_t)cnt * sizeof(ecl_hit)));
+  } else {
+    // Dense filter (e.g. the all-ones dump filter): redo the span in slices whose worst case fits the ring.
+    CKA(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
+    const u64 slice = std::max<u64>(1, dev->hit_cap / (MAX_HITS_PER_KEY * GROUP_KEYS)) * GROUP_KEYS;
+    int rc = launch_add(dev, 0, dev->p_keys, slice, true, &dev->result);
+    if (rc) return abandon(dev, rc);
+  }
+  std::sort(dev->result.begin(), dev->result.end(), hit_less_add);
+  return ECL_OK;
+}
+
+static int collect_mul(ecl_dev *dev, mul_slot &s) {
+  CKA(cudaEventSynchronize(s.ev_end));
+  float ms = 0;
+  CKA(cudaEventElapsedTime(&ms, s.ev_begin, s.ev_end));
+  dev->last_total_ms = ms;
+  CKA(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+  dev->last_hot_ms = ms;
+  dev->last_launches = 2;
+  const u32 cnt = *s.h_count;
+  dev->result.clear();
+  if (cnt <= dev->hit_cap) {
+    dev->result.resize(cnt);
+    if (cnt) {  // on the io stream: a younger submit may be computing on dev->stream, this batch is complete (ev_end)
+      CKA(cudaMemcpyAsync(dev->result.data(), s.d_hits, (size_t)cnt * sizeof(ecl_hit), cudaMemcpyDeviceToHost, dev->io_stream));
+      CKA(cudaStreamSynchronize(dev->io_stream));
+    }
+  } else {
+    // dense filter: the points are still in the slot's scratch, only the hashing is redone, in slices that fit the ring
+    const u32 slice = dev->hit_cap / 2;
+    for (u32 b = 0; b < s.n; b += slice) {
+      CKA(cudaMemsetAsync(s.d_hit_count, 0, sizeof(u32), dev->stream));
+      int rc = launch_mul_hash(dev, s, b, std::min<u32>(s.n, b + slice));
+      if (rc) return abandon(dev, rc);
+      u32 c2 = 0;
+      CKA(fetch(dev, &c2, s.d_hit_count, sizeof c2));
+      const size_t old = dev->result.size();
+      dev->result.resize(old + c2);
+      if (c2) CKA(fetch(dev, dev->result.data() + old, s.d_hits, (size_t)c2 * sizeof(ecl_hit)));
+    }
+  }
+  std::sort(dev->result.begin(), dev->result.end(), hit_less_mul);
+  return ECL_OK;
+}
+
 extern "C" int ecl_collect(ecl_dev *dev, ecl_hit *hits, uint32_t cap, uint32_t *n_hits, uint64_t *keys_done) {
   if (!dev) return ECL_E_ARG;
   if (!dev->pending) return fail(dev, ECL_E_STATE, "ecl_collect without a pending submit");
-  CK(cudaSetDevice(dev->ordinal));
+  CKA(cudaSetDevice(dev->ordinal));
   if (!dev->result_ready) {
-    CK(cudaStreamSynchronize(dev->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, dev->ev_begin, dev->ev_end));
-    dev->last_total_ms = ms;
-    dev->last_hot_ms = 0;
-    for (size_t i = 0; i + 1 < dev->ev_used; i += 2) {
-      CK(cudaEventElapsedTime(&ms, dev->ev_pool[i], dev->ev_pool[i + 1]));
-      dev->last_hot_ms += ms;
-    }
-    dev->last_launches = dev->launches;
-    if (dev->pending == 1 && dev->cand_counts && !dev->force_inline) {
-      // the asynchronous probe's candidate queue overflowed (a filter far denser than a bloom filter should be):
-      // nothing may be lost, so the span is redone with the probes inline
-      u32 ovf = 0;
-      CK(cudaMemcpy(&ovf, dev->cand_counts + dev->sm_count, sizeof ovf, cudaMemcpyDeviceToHost));
-      if (ovf) {
-        dev->force_inline = true;
-        CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
-        int rc2 = launch_add(dev, 0, dev->p_keys / GROUP_KEYS, (u64)dev->Tmax * dev->groups_per_thread, false, nullptr);
-        if (rc2) {
-          dev->pending = 0;
-          return rc2;
-        }
-        CK(cudaStreamSynchronize(dev->stream));
-      }
-    }
-    u32 cnt = 0;
-    CK(cudaMemcpy(&cnt, dev->d_hit_count, sizeof cnt, cudaMemcpyDeviceToHost));
-    dev->result.clear();
-    if (cnt <= dev->hit_cap) {
-      dev->result.resize(cnt);
-      if (cnt) CK(cudaMemcpy(dev->result.data(), dev->d_hits, (size_t)cnt * sizeof(ecl_hit), cudaMemcpyDeviceToHost));
-    } else {
-      // Dense filter (e.g. the all-ones dump filter): redo the span in slices whose worst case fits the ring.
-      CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
-      int rc;
-      if (dev->pending == 1) {
-        const u64 slice = std::max<u64>(1, dev->hit_cap / (MAX_HITS_PER_KEY * GROUP_KEYS));
-        rc = launch_add(dev, 0, dev->p_keys / GROUP_KEYS, slice, true, &dev->result);
-      } else {
-        rc = ECL_OK;
-        const u32 slice = dev->hit_cap / 2;
-        for (u32 b = 0; b < (u32)dev->p_keys && rc == ECL_OK; b += slice) {
-          rc = launch_mul(dev, b, std::min<u32>((u32)dev->p_keys, b + slice));
-          if (rc) break;
-          CK(cudaStreamSynchronize(dev->stream));
-          u32 c2 = 0;
-          CK(cudaMemcpy(&c2, dev->d_hit_count, sizeof c2, cudaMemcpyDeviceToHost));
-          const size_t old = dev->result.size();
-          dev->result.resize(old + c2);
-          if (c2) CK(cudaMemcpy(dev->result.data() + old, dev->d_hits, (size_t)c2 * sizeof(ecl_hit), cudaMemcpyDeviceToHost));
-          for (size_t i = old; i < dev->result.size(); ++i) dev->result[i].key_off += b;
-          CK(cudaMemsetAsync(dev->d_hit_count, 0, sizeof(u32), dev->stream));
-        }
-      }
-      if (rc) {
-        dev->pending = 0;
-        return rc;
-      }
-    }
-    std::sort(dev->result.begin(), dev->result.end(), dev->pending == 1 ? hit_less_add : hit_less_mul);
+    int rc = dev->pending == 1 ? collect_add(dev) : collect_mul(dev, dev->mslot[dev->m_head]);
+    if (rc) return rc;
     dev->result_ready = true;
   }
+  const u64 done = dev->pending == 1 ? dev->p_keys : dev->mslot[dev->m_head].n;
   if (n_hits) *n_hits = (u32)std::min<size_t>(dev->result.size(), cap);
-  if (keys_done) *keys_done = dev->p_keys;
-  if (dev->result.size() > cap)
+  if (keys_done) *keys_done = done;
+  if (dev->result.size() > cap)  // the work is kept: the caller comes back with a larger buffer
     return fail(dev, ECL_E_OVERFLOW, "%zu hits do not fit the caller's buffer of %u; call ecl_collect again with a larger one", dev->result.size(), cap);
   if (hits && !dev->result.empty()) memcpy(hits, dev->result.data(), dev->result.size() * sizeof(ecl_hit));
-  dev->pending = 0;
+  dev->result_ready = false;
+  if (dev->pending == 2) {
+    dev->mslot[dev->m_head].busy = false;
+    dev->m_head = (dev->m_head + 1) % ECL_MUL_DEPTH;
+    if (--dev->m_count == 0) dev->pending = 0;
+  } else {
+    dev->pending = 0;
+  }
   return ECL_OK;
 }
 
@@ -631,6 +945,8 @@ extern "C" int ecl_last_elapsed_ms(ecl_dev *dev, float *total_ms, float *hot_ker
 }
 
 // ---------------------------------------------------------------- primitives (parity entry points)
+// Uploads, kernel and downloads all go through dev->stream (created non-blocking: it does not order with the legacy
+// default stream, and a pageable cudaMemcpy may return before its DMA has landed).
 
 template <typename T>
 struct DevBuf {
@@ -638,6 +954,8 @@ struct DevBuf {
   ~DevBuf() { cudaFree(p); }
   cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(T)); }
 };
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream))
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream))
 
 extern "C" int ecl_prim_fp(ecl_dev *dev, int op, const uint64_t (*a)[4], const uint64_t (*b)[4], uint64_t (*out)[4], uint32_t n) {
   if (!dev || !a || !out || n == 0) return fail(dev, ECL_E_ARG, "ecl_prim_fp: bad arguments");
@@ -645,15 +963,15 @@ extern "C" int ecl_prim_fp(ecl_dev *dev, int op, const uint64_t (*a)[4], const u
   DevBuf<fe> da, db, dout;
   CK(da.alloc(n));
   CK(dout.alloc(n));
-  CK(cudaMemcpy(da.p, a, (size_t)n * 32, cudaMemcpyHostToDevice));
+  H2D(da.p, a, (size_t)n * 32);
   if (b) {
     CK(db.alloc(n));
-    CK(cudaMemcpy(db.p, b, (size_t)n * 32, cudaMemcpyHostToDevice));
+    H2D(db.p, b, (size_t)n * 32);
   }
   prim_fp_kernel<<<(n + 127) / 128, 128, 0, dev->stream>>>(op, da.p, db.p, dout.p, n);
   CK(cudaGetLastError());
+  D2H(out, dout.p, (size_t)n * 32);
   CK(cudaStreamSynchronize(dev->stream));
-  CK(cudaMemcpy(out, dout.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
   return ECL_OK;
 }
 
@@ -664,14 +982,14 @@ extern "C" int ecl_prim_scalar_mul(ecl_dev *dev, const uint64_t (*k)[4], uint64_
   DevBuf<u32> dout;
   CK(dk.alloc(n));
   CK(dout.alloc((size_t)n * 16));
-  CK(cudaMemcpy(dk.p, k, (size_t)n * 32, cudaMemcpyHostToDevice));
+  H2D(dk.p, k, (size_t)n * 32);
   SmulParams sp;
   memset(&sp, 0, sizeof sp);
   sp.scalars = dk.p, sp.gtab = dev->gtab, sp.count = n, sp.mode = 2, sp.out = dout.p;
   smul_kernel<<<(n + 127) / 128, 128, 0, dev->stream>>>(sp);
   CK(cudaGetLastError());
+  D2H(out_xy, dout.p, (size_t)n * 64);
   CK(cudaStreamSynchronize(dev->stream));
-  CK(cudaMemcpy(out_xy, dout.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
   return ECL_OK;
 }
 
@@ -680,14 +998,14 @@ extern "C" int ecl_prim_hash160(ecl_dev *dev, const uint64_t (*xy)[8], uint32_t 
   CK(cudaSetDevice(dev->ordinal));
   DevBuf<u32> dxy, d33, d65;
   CK(dxy.alloc((size_t)n * 16));
-  CK(cudaMemcpy(dxy.p, xy, (size_t)n * 64, cudaMemcpyHostToDevice));
+  H2D(dxy.p, xy, (size_t)n * 64);
   if (out33) CK(d33.alloc((size_t)n * 5));
   if (out65) CK(d65.alloc((size_t)n * 5));
   prim_hash160_kernel<<<(n + 127) / 128, 128, 0, dev->stream>>>(dxy.p, d33.p, d65.p, n);
   CK(cudaGetLastError());
+  if (out33) D2H(out33, d33.p, (size_t)n * 20);
+  if (out65) D2H(out65, d65.p, (size_t)n * 20);
   CK(cudaStreamSynchronize(dev->stream));
-  if (out33) CK(cudaMemcpy(out33, d33.p, (size_t)n * 20, cudaMemcpyDeviceToHost));
-  if (out65) CK(cudaMemcpy(out65, d65.p, (size_t)n * 20, cudaMemcpyDeviceToHost));
   return ECL_OK;
 }
 
@@ -699,11 +1017,11 @@ extern "C" int ecl_prim_bloom(ecl_dev *dev, const uint32_t (*h160)[5], uint8_t *
   DevBuf<uint8_t> dout;
   CK(dh.alloc((size_t)n * 5));
   CK(dout.alloc(n));
-  CK(cudaMemcpy(dh.p, h160, (size_t)n * 20, cudaMemcpyHostToDevice));
+  H2D(dh.p, h160, (size_t)n * 20);
   prim_bloom_kernel<<<(n + 127) / 128, 128, 0, dev->stream>>>(bloom_view(dev), dh.p, dout.p, n);
   CK(cudaGetLastError());
+  D2H(out, dout.p, n);
   CK(cudaStreamSynchronize(dev->stream));
-  CK(cudaMemcpy(out, dout.p, n, cudaMemcpyDeviceToHost));
   return ECL_OK;
 }
 
@@ -714,13 +1032,13 @@ static int run_peak(ecl_dev *dev, double *gops, double *mhz) {
   DevBuf<u32> out;
   DevBuf<unsigned long long> cyc;
   CK(out.alloc(1024));
-  CK(cyc.alloc(1));
+  CK(cyc.alloc(2));
   const int blocks = dev->sm_count * 8;  // 8 x 256 threads = 2048 threads per SM: full occupancy
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   float best = 1e30f;
-  unsigned long long cycles = 0;
+  unsigned long long cycles[2] = {0, 1};
   for (int rep = 0; rep < 5; ++rep) {
     CK(cudaEventRecord(e0, dev->stream));
     peak_kernel<KIND><<<blocks, 256, 0, dev->stream>>>(out.p, 0x1234567u + rep, cyc.p);
@@ -730,18 +1048,20 @@ static int run_peak(ecl_dev *dev, double *gops, double *mhz) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     if (rep > 0 && ms < best) {
       best = ms;
-      CK(cudaMemcpy(&cycles, cyc.p, sizeof cycles, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpyAsync(cycles, cyc.p, sizeof cycles, cudaMemcpyDeviceToHost, dev->stream));
+      CK(cudaStreamSynchronize(dev->stream));
     }
   }
   cudaEventDestroy(e0), cudaEventDestroy(e1);
   const double insts = (double)blocks * 256.0 * PEAK_ITERS * PEAK_UNROLL * PEAK_CHAINS;
   *gops = insts / (best * 1e-3) / 1e9;
-  // one block's loop time in cycles over the kernel's wall time underestimates the clock when blocks run in
-  // waves; with 8 blocks/SM all resident it is one wave, so cycles/time ~ SM clock
-  *mhz = (double)cycles / (best * 1e-3) / 1e6;
+  // SM clock: cycle counter over the nanosecond timer, both read by the same thread around its loop (the ratio of one
+  // block's cycles to the kernel's wall time is only the clock when all blocks run as one wave)
+  *mhz = cycles[1] ? (double)cycles[0] / (double)cycles[1] * 1e3 : 0.0;
   return ECL_OK;
 }
 
+#ifdef ECL_EXPERIMENTAL
 template <int KIND, int FILL>
 static int run_mulbench(ecl_dev *dev, double *gmuls) {
   DevBuf<u32> out;
@@ -763,8 +1083,9 @@ static int run_mulbench(ecl_dev *dev, double *gmuls) {
   *gmuls = (double)dev->sm_count * 512.0 * MULBENCH_ITERS * 2.0 / (best * 1e-3) / 1e9;
   return ECL_OK;
 }
+#endif
 
-// one kind of peak.cuh by number (0..18), or a field-multiplication throughput (19..22, fp64mul.cuh); see ecl_peak_kinds in ecloop_b200/__init__.py for the names
+// one kind of peak.cuh by number (0..18); see PEAK_KINDS in ecloop_b200/__init__.py for the names
 extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double *sm_mhz) {
   if (!dev || !gops) return ECL_E_ARG;
   CK(cudaSetDevice(dev->ordinal));
@@ -790,10 +1111,14 @@ extern "C" int ecl_peak_bench_kind(ecl_dev *dev, int kind, double *gops, double 
   case 16: rc = run_peak<16>(dev, gops, &mhz); break;
   case 17: rc = run_peak<17>(dev, gops, &mhz); break;
   case 18: rc = run_peak<18>(dev, gops, &mhz); break;
+#ifdef ECL_EXPERIMENTAL
+  // field multiplications per second (G mul/s) of fe_mul (IMAD.WIDE) / fe6_mul (DFMA), alone (19, 20) and with
+  // 384 LOP3/SHF per multiplication beside them (21, 22), 512 threads per SM like the add kernel
   case 19: rc = run_mulbench<0, 0>(dev, gops); break;
   case 20: rc = run_mulbench<1, 0>(dev, gops); break;
   case 21: rc = run_mulbench<0, 384>(dev, gops); break;
   case 22: rc = run_mulbench<1, 384>(dev, gops); break;
+#endif
   default: return fail(dev, ECL_E_ARG, "unknown peak kind %d", kind);
   }
   if (sm_mhz) *sm_mhz = mhz;

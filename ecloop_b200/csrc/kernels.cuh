@@ -1,7 +1,8 @@
 // kernels.cuh — the small sm_100a kernels behind the C-ABI (the fused add kernel lives in add_kernel.cuh and is
 // compiled one variant per translation unit, add_inst.cu):
 //
-//   mul_kernel<A33,A65>          K2: ec_gtable_mul + normalise + hash160 + blf_has (main.c:531-534)
+//   mul_points_kernel            K2a: ec_gtable_mul + ec_jacobi_grprdc (main.c:531-532)
+//   mul_hash_kernel<A33,A65,NW>  K2b: check_found_mul (main.c:458-484): hash160 + blf_has
 //   smul_kernel                  K3: k*G for generated or given scalars -> +-i*s*G table / thread centres
 //                                (ctx_precompute_gpoints main.c:219-246, GStart main.c:359-360)
 //   gtab_bases/gtab_fill         one-off window table d * 2^(16 w) * G (ec_gtable_init, lib/ecc.c:880-905)
@@ -9,7 +10,9 @@
 #pragma once
 #include "add_kernel.cuh"
 #include "common.cuh"
-#include "fp64mul.cuh"
+#ifdef ECL_EXPERIMENTAL
+#include "fp64mul.cuh"  // FP64-pipe field arithmetic: parity-tested experiment, not on the hot path, not in the product library
+#endif
 
 // ---------------------------------------------------------------- K3: scalar multiples of G
 
@@ -22,10 +25,19 @@ struct SmulParams {
              // 1: thread centres (m = j), SoA out with stride `count`
              // 2: explicit scalars, AoS out (zeros for the point at infinity)
   u32 *out;
+  fe extra_k;      // thread `count` (one past the last) computes extra_k * G, AoS, into extra_out when that is set:
+  u32 *extra_out;  // the group step 2*Hr*s*G of an add launch whose Hr has no table entry (ecl_api.cu plan_launch)
 };
 
 __global__ void __launch_bounds__(128) smul_kernel(const SmulParams p) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == p.count && p.extra_out) {
+    jac a;
+    fe x = fe_zero(), y = fe_zero();
+    if (gtab_mul(a, p.extra_k, p.gtab)) jac_to_affine(x, y, a);
+    for (int l = 0; l < 8; ++l) p.extra_out[l] = x.v[l], p.extra_out[8 + l] = y.v[l];
+    return;
+  }
   if (j >= p.count) return;
   fe k;
   if (p.mode == 2) k = p.scalars[j];
@@ -45,13 +57,19 @@ __global__ void __launch_bounds__(128) smul_kernel(const SmulParams p) {
 }
 
 // ---------------------------------------------------------------- K2: mul path
+// ec_gtable_mul x n + ec_jacobi_grprdc + check_found_mul (main.c:531-534) as two kernels with different shapes:
+//   K2a mul_points_kernel   field work only (FMA + ALU pipes, 100 registers): k*G per key from the window table in
+//                           Jacobian coordinates, then the batch normalisation of lib/ecc.c:695-707 per thread (B keys
+//                           share one Fermat inversion); affine (x, y) go back into the key's scratch slot;
+//   K2b mul_hash_kernel     hashing only (ALU pipe): SHA-256 -> RIPEMD-160 of the 33 / 65 byte encodings + bloom probe,
+//                           one CTA of 512 threads per SM in lockstep like the add kernel, filter in shared memory when
+//                           it fits.
+// Between them 64 B per key are written and read once (coalesced): 0.13 KB/key against ~25 k integer operations.
 
 struct MulParams {
   const fe *scalars;
   const uint4 *gtab;
-  uint4 *scratch;  // per key 8 x 16 B (X, Y, Z, prefix product), slot-major: [(m*8 + q)*T + t]
-  BloomView bloom;
-  HitSink sink;
+  uint4 *scratch;  // per key 8 x 16 B (X, Y, Z, prefix product; X, Y become affine x, y), slot-major: [(m*8 + q)*T + t]
   u32 count;  // keys
   u32 T;      // threads that own keys
   u32 B;      // keys per thread: thread t owns keys m*T + t, m < B (coalesced scalar loads)
@@ -63,13 +81,43 @@ __device__ __forceinline__ void st_fe(uint4 *p, size_t stride, const fe &a) {
 }
 __device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_from_u4(p[0], p[stride]); }
 
-// ec_gtable_mul x n + ec_jacobi_grprdc + check_found_mul (main.c:531-534). The reference normalises a job of
-// 2048 projective points with ONE inversion (lib/ecc.c:695-707); here every thread does the same over its own B
-// keys: pass 1 computes k*G in Jacobian coordinates and the running product of the Z's (X, Y, Z and the prefix
-// go to a coalesced scratch), one Fermat inversion per thread, pass 2 peels 1/Z off from the far end, converts
-// to affine, hashes and probes. A key = 0 (mod n) has no point: it rides along as Z = 1 and is skipped.
-template <bool A33, bool A65>
-__global__ void __launch_bounds__(128) mul_kernel(const MulParams p) {
+// acc = k*G like gtab_mul (ec.cuh) with the field multiplications inlined into ONE loop body (the setup-path gtab_mul
+// calls fe_mul out of line through memory: fine for 75 000 centres per launch, 40 % of the time here).
+// The first non-zero window is a load; the second is an affine + affine addition (4M + 2S); the rest are mixed
+// additions (8M + 3S). Returns false for k = 0 (mod n).
+static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
+  int have = 0;
+#pragma unroll 1
+  for (int w = 0; w < GTAB_WINDOWS; ++w) {
+    const u32 d = (k.v[w >> 1] >> ((w & 1) * 16)) & 0xffffu;
+    if (d == 0) continue;
+    fe qx, qy;
+    gtab_load(qx, qy, gtab, (u32)w * GTAB_PER_WIN + d - 1);
+    if (!have) {
+      acc.x = qx, acc.y = qy, acc.z = fe_one();
+      have = 1;
+      continue;
+    }
+    // mixed addition; with Z1 = 1 the first three products are copies, kept in one code path by multiplying by one:
+    // the second window is 1 of 15 additions, a separate body would double the loop for a 3 % gain
+    const fe z2 = fe_sqr(acc.z);
+    const fe u2 = fe_mul(qx, z2);
+    const fe s2 = fe_mul(fe_mul(qy, z2), acc.z);
+    const fe h = fe_sub(u2, acc.x);
+    const fe rr = fe_sub(s2, acc.y);
+    const fe h2 = fe_sqr(h);
+    const fe h3 = fe_mul(h2, h);
+    const fe v = fe_mul(acc.x, h2);
+    const fe x3 = fe_sub(fe_sub(fe_sub(fe_sqr(rr), h3), v), v);
+    const fe y3 = fe_sub(fe_mul(rr, fe_sub(v, x3)), fe_mul(acc.y, h3));
+    const fe z3 = fe_mul(acc.z, h);
+    if (fe_is_zero(z3)) return false;  // k = n lands on -acc at the top window: infinity
+    acc.x = x3, acc.y = y3, acc.z = z3;
+  }
+  return have != 0;
+}
+
+__global__ void __launch_bounds__(256) mul_points_kernel(const MulParams p) {
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.T) return;
   const size_t T = p.T;
@@ -80,28 +128,75 @@ __global__ void __launch_bounds__(128) mul_kernel(const MulParams p) {
     const u32 j = m * p.T + t;
     jac a;
     bool ok = false;
-    if (j < p.count) ok = gtab_mul(a, p.scalars[j], p.gtab);
+    if (j < p.count) ok = gtab_mul_fast(a, p.scalars[j], p.gtab);
     if (!ok) a.x = fe_zero(), a.y = fe_zero(), a.z = fe_one();
     uint4 *slot = scr + (size_t)m * 8 * T;
     st_fe(slot, T, a.x), st_fe(slot + 2 * T, T, a.y), st_fe(slot + 4 * T, T, a.z), st_fe(slot + 6 * T, T, acc);
-    acc = fe_mul_noinline(acc, a.z);
+    acc = fe_mul(acc, a.z);
   }
   fe inv = fe_inv(acc);
 #pragma unroll 1
   for (int m = (int)p.B - 1; m >= 0; --m) {
-    const uint4 *slot = scr + (size_t)m * 8 * T;
+    uint4 *slot = scr + (size_t)m * 8 * T;
     const fe z = ld_fe(slot + 4 * T, T), pre = ld_fe(slot + 6 * T, T);
-    const fe zi = fe_mul_noinline(inv, pre);
-    inv = fe_mul_noinline(inv, z);
+    const fe zi = fe_mul(inv, pre);
+    inv = fe_mul(inv, z);
     const fe ax = ld_fe(slot, T), ay = ld_fe(slot + 2 * T, T);
-    if (fe_is_zero(ax) && fe_is_zero(ay)) continue;  // no point for this slot
-    const fe zi2 = fe_mul_noinline(zi, zi);
-    const fe fx = fe_mul_noinline(ax, zi2), fy = fe_mul_noinline(ay, fe_mul_noinline(zi2, zi));
-    u32 x[1][8], y[1][8];
+    const fe zi2 = fe_sqr(zi);
+    st_fe(slot, T, fe_mul(ax, zi2));  // (0, 0) stays (0, 0): "no point for this key"
+    st_fe(slot + 2 * T, T, fe_mul(ay, fe_mul(zi2, zi)));
+  }
+}
+
+struct MulHashParams {
+  const uint4 *scratch;  // affine x, y of key j = m*T + t at [(m*8 + {0,1 | 2,3})*T + t]
+  BloomView bloom;
+  u32 bloom_smem_words;  // != 0: staged into shared memory
+  HitSink sink;
+  u32 T;
+  u32 begin, end;  // keys [begin, end) of the batch
+};
+
+template <bool A33, bool A65, int NW>
+__global__ void __launch_bounds__(512, 1) mul_hash_kernel(const MulHashParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) u64 mbar;
+  u64 *sbloom = reinterpret_cast<u64 *>(smem_raw);
+  BloomView bv = p.bloom;
+  if (p.bloom_smem_words) {
+    const u32 bytes = ((p.bloom_smem_words * 8u + 15u) / 16u) * 16u;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, bytes);
+      bulk_g2s(sbloom, p.bloom.bits, bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    bv.bits = sbloom;
+  }
+  const u32 lanes = gridDim.x * blockDim.x * NW;
+  const u32 n = p.end - p.begin;
+  const u32 rounds = (n + lanes - 1) / lanes;  // the same for every thread: the CTA stays in lockstep
+#pragma unroll 1
+  for (u32 r = 0; r < rounds; ++r) {
+    __syncthreads();
+    u32 x[NW][8], y[NW][8];
+    u64 off[NW];
+    bool act[NW];
 #pragma unroll
-    for (int l = 0; l < 8; ++l) x[0][l] = fx.v[l], y[0][l] = fy.v[l];
-    const u64 off[1] = {(u64)m * p.T + t};
-    check_points<1, A33, A65, false>(p.bloom, p.sink, x, y, off);
+    for (int w = 0; w < NW; ++w) {
+      const u32 i = r * lanes + (u32)w * (lanes / NW) + blockIdx.x * blockDim.x + threadIdx.x;
+      const u32 j = p.begin + (i < n ? i : n - 1);
+      const u32 m = j / p.T, t = j - m * p.T;
+      const uint4 *slot = p.scratch + (size_t)m * 8 * p.T + t;
+      const fe fx = ld_fe(slot, p.T), fy = ld_fe(slot + 2 * (size_t)p.T, p.T);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) x[w][l] = fx.v[l], y[w][l] = fy.v[l];
+      off[w] = j;
+      act[w] = i < n && !(fe_is_zero(fx) && fe_is_zero(fy));
+    }
+    NoPipe none;
+    check_points<NW, A33, A65, false, 1>(bv, p.sink, x, y, off, act, none);
   }
 }
 
@@ -173,6 +268,7 @@ __global__ void prim_fp_kernel(int op, const fe *a, const fe *b, fe *out, u32 n)
   case ECL_OP_ADD: r = fe_add(x, y); break;
   case ECL_OP_SUB: r = fe_sub(x, y); break;
   case ECL_OP_NEG: r = fe_neg(x); break;
+#ifdef ECL_EXPERIMENTAL
   case ECL_OP_MUL_F64: r = fe6_to_fe(fe6_mul(fe6_from_fe(x), fe6_from_fe(y))); break;
   case ECL_OP_MUL_F64_CHAIN: {  // x * y^16 without leaving the weak 44-bit-limb form in between
     fe6 acc = fe6_from_fe(x);
@@ -196,6 +292,7 @@ __global__ void prim_fp_kernel(int op, const fe *a, const fe *b, fe *out, u32 n)
     r = fe6_to_fe(op == ECL_OP_AFFINE_F64_X ? rx : ry);
     break;
   }
+#endif
   default: r = fe_inv(x); break;
   }
   out[i] = r;

@@ -115,6 +115,30 @@ struct ProbePipe {
     ++n;
   }
 
+  // Run-time slot WITH the L2 evict-first hint (two-phase instances that hash one point at a time, NW = 1): the slot's
+  // byte offset goes through an opaque move so that ptxas sees one plain vector register as the shared address
+  // (see cp_async_16: the [R+UR+imm] form it may pick otherwise is broken in CUDA 12.9).
+  __device__ __forceinline__ void submit_rt(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
+    const u32 slot = n % PP_DEPTH;
+    if (n >= PP_DEPTH) {
+      cp_async_wait<PP_DEPTH - 1>();
+      retire(slot);
+    }
+    const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
+    const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
+    const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
+    u32 dst = probe_s32 + slot * (2u * THREADS * 16u);
+    asm volatile("mov.b32 %0, %0;" : "+r"(dst));
+    cp_async_16(dst, bv.bits + (i0 & ~1ull), policy);
+    cp_async_16(dst + THREADS * 16u, bv.bits + (i1 & ~1ull), policy);
+    cp_async_commit();
+    const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
+    meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
+    meta[(slot * 2 + 1) * THREADS] =
+        make_uint4(h[4], (u32)off, (u32)(off >> 32), endo | (kind << 8) | ((active ? 1u : 0u) << 16) | (p0 << 17) | (p1 << 24));
+    ++n;
+  }
+
   // Variant for the software-pipelined kernel: run-time slot, no cache hint. That kernel's 7 000-instruction basic
   // blocks are sensitive to what ptxas makes of any change here (5 840 vs 4 560 Mkeys/s for equivalent forms), its
   // loop is small enough to stay in L2 beside the probe traffic, and this is the form measured at 5 840.
@@ -152,6 +176,12 @@ template <u32 SLOT, int THREADS>
 __device__ __forceinline__ void probe_hash(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
                                            u64 off, u32 endo, u32 kind, bool active) {
   pipe.template submit<SLOT>(hh, off, endo, kind, active);
+}
+
+template <int THREADS>
+__device__ __forceinline__ void probe_hash_rt(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
+                                              u64 off, u32 endo, u32 kind, bool active) {
+  pipe.submit_rt(hh, off, endo, kind, active);
 }
 
 template <int THREADS>

@@ -44,7 +44,7 @@ static int gen_usage(const char *name) {
   return 1;
 }
 
-int blf_gen_main(int argc, const char **argv) {
+int blf_gen_args(int argc, const char **argv, blf_gen_plan *out) {
   const char *nraw = NULL;
   for (int i = 1; i < argc - 1; ++i)
     if (strcmp(argv[i], "-n") == 0) {
@@ -67,7 +67,20 @@ int blf_gen_main(int argc, const char **argv) {
   const double p = 1.0 / (double)r;
   const unsigned long long m = (unsigned long long)((double)n * log(p) / log(1.0 / pow(2.0, log(2.0))));
   const double mb = (double)m / 8 / 1024 / 1024;
-  const uint64_t size = (m + 63) / 64;
+  out->n = n, out->r = r, out->m = m, out->mb = mb, out->size = (m + 63) / 64, out->path = path;
+  return 0;
+}
+
+void blf_hex40_words(uint32_t h[5], const char *s) { words_from_hex40(h, s); }
+
+int blf_gen_main(int argc, const char **argv) {
+  blf_gen_plan plan;
+  const int rc = blf_gen_args(argc, argv, &plan);
+  if (rc) return rc;
+  const unsigned long long n = plan.n, r = plan.r, m = plan.m;
+  const double mb = plan.mb;
+  const uint64_t size = plan.size;
+  const char *path = plan.path;
 
   ecl_filter f = {0};
   if (access(path, F_OK) == 0) {

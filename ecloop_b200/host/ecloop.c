@@ -404,13 +404,16 @@ static void cmd_rnd(app *a) {
 
 /* The reference reads stdin with fgets on one thread and parses on the workers (main.c:549-569, 503-527). At GPU
  * speed the text side is the bottleneck (10 M keys = 650 MB of hex), so the feeder is a three-stage pipeline:
- *   reader (main thread)   fread()s large blocks, cuts them at a line boundary, numbers them;
+ *   reader thread          read()s large blocks, cuts them at a line boundary, numbers them;
  *   parser threads (-t)    split a block into lines with the reference's rules and turn each into a key;
- *   rank threads (per GPU) take parsed blocks IN SEQUENCE ORDER, fuse them into submits of up to 2^20 keys.
- * With one GPU the found lines therefore come out in input order, like `-t 1`. */
+ *   rank threads (per GPU) take parsed blocks IN SEQUENCE ORDER, fuse them into submits of up to 2^20 keys and keep
+ *                          TWO submits in flight (ECL_MUL_DEPTH): the upload and kernels of one batch run while the
+ *                          previous batch's hits are reported and the next one is gathered.
+ * Reader and parsers start BEFORE the GPUs are opened (setup), so context creation and the window-table build overlap
+ * with reading and parsing. With one GPU the found lines come out in input order, like `-t 1`. */
 
 #define MUL_BLOCK_BYTES (8u << 20)
-#define MUL_RING 16 /* blocks in flight */
+#define MUL_RING 64 /* blocks in flight: up to 512 MB of text may be parsed ahead while the devices come up */
 
 typedef struct mul_block {
   char *text;          /* raw bytes, whole lines (the last block may lack the final newline) */
@@ -428,6 +431,8 @@ typedef struct mul_pipe {
   uint32_t take_off;                      /* keys of block seq_take already handed out */
   bool eof;
   pthread_cond_t cv;
+  pthread_t reader_th, parse_th[64];
+  int n_parsers;
   uint64_t us_read, us_parse, us_gpu, us_report; /* stage totals for ECLOOP_VERBOSE */
 } mul_pipe;
 
@@ -455,79 +460,13 @@ static void *mul_parser_main(void *p) {
   }
 }
 
-static void *mul_rank_main(void *p) {
-  mul_pipe *mp = ((rank_arg *)p)->a->mul;
+/* reader: blocks of whole lines; the tail after the last newline moves to the front of the next block */
+static void *mul_reader_main(void *p) {
+  mul_pipe *mp = p;
   app *a = mp->a;
-  ecl_dev *dev = a->dev[((rank_arg *)p)->rank];
-  hit_buf hb = {0};
-  uint64_t(*keys)[4] = malloc((size_t)MUL_BATCH_KEYS * sizeof *keys);
-  if (!keys) die("out of memory");
-  for (;;) {
-    /* take parsed blocks in sequence order until the submit is full */
-    uint32_t n = 0;
-    pthread_mutex_lock(&a->mu);
-    for (;;) {
-      mul_block *b = &mp->ring[mp->seq_take % MUL_RING];
-      const bool ready = mp->seq_take < mp->seq_read && b->state == 3;
-      if (ready) { /* a block of very short lines can hold more keys than one submit: take it in parts */
-        const uint32_t avail = b->count - mp->take_off, room = MUL_BATCH_KEYS - n, k = avail < room ? avail : room;
-        memcpy(keys + n, b->keys + mp->take_off, (size_t)k * sizeof *keys);
-        n += k, mp->take_off += k;
-        if (mp->take_off == b->count) {
-          b->state = 0, mp->take_off = 0;
-          mp->seq_take++;
-          pthread_cond_broadcast(&mp->cv);
-        }
-        if (n == MUL_BATCH_KEYS) break;
-        continue;
-      }
-      if (n || a->fatal) break;                           /* something to do (or giving up) */
-      if (mp->eof && mp->seq_take == mp->seq_read) break; /* drained */
-      pthread_cond_wait(&mp->cv, &a->mu);
-    }
-    pthread_mutex_unlock(&a->mu);
-    if (!n || a->fatal) break;
-    uint32_t nh = 0;
-    const uint64_t t0 = now_us();
-    if (ecl_mul_submit(dev, (const uint64_t(*)[4])keys, n, a->flags & (ECL_A33 | ECL_A65)) != ECL_OK) {
-      fprintf(stderr, "ecloop: GPU error: %s\n", ecl_last_error(dev));
-      a->fatal = 1;
-    } else if (collect_hits(a, dev, &hb, &nh) == 0) {
-      const uint64_t t1 = now_us();
-      for (uint32_t i = 0; i < nh; ++i) /* check_found_mul (main.c:458-479): no verification on this path */
-        if (filter_exact(&a->filter, hb.hits[i].h160)) write_found(a, hb.hits[i].kind, hb.hits[i].h160, keys[hb.hits[i].key_off]);
-      progress_add(a, n);
-      pthread_mutex_lock(&a->mu);
-      mp->us_gpu += t1 - t0, mp->us_report += now_us() - t1;
-      pthread_mutex_unlock(&a->mu);
-    }
-    if (a->fatal) {
-      pthread_mutex_lock(&a->mu);
-      pthread_cond_broadcast(&mp->cv);
-      pthread_mutex_unlock(&a->mu);
-      break;
-    }
-  }
-  free(keys);
-  free(hb.hits), free(hb.pks), free(hb.xy), free(hb.h33), free(hb.h65);
-  return NULL;
-}
-
-static void cmd_mul(app *a) {
-  static mul_pipe pipe;
-  mul_pipe *mp = &pipe;
-  mp->a = a, a->mul = mp;
-  pthread_cond_init(&mp->cv, NULL);
-  pthread_t rank_th[64], parse_th[64];
-  rank_arg arg[64];
-  int n_parsers = (int)(a->threads_shown < 16 ? a->threads_shown : 16);
-  for (int i = 0; i < n_parsers; ++i) pthread_create(&parse_th[i], NULL, mul_parser_main, mp);
-  for (int r = 0; r < a->n_gpus; ++r) {
-    arg[r].a = a, arg[r].rank = r;
-    pthread_create(&rank_th[r], NULL, mul_rank_main, &arg[r]);
-  }
-
-  /* reader: blocks of whole lines; the tail after the last newline moves to the front of the next block */
+#ifdef F_SETPIPE_SZ
+  fcntl(STDIN_FILENO, F_SETPIPE_SZ, 1 << 20); /* a pipe's default 64 KB costs a wake-up per 1000 keys; ignored for files */
+#endif
   char *carry = malloc(MUL_BLOCK_BYTES + 2);
   size_t carry_len = 0;
   if (!carry) die("out of memory");
@@ -542,10 +481,16 @@ static void cmd_mul(app *a) {
     size_t have = carry_len;
     carry_len = 0;
     const uint64_t tr = now_us();
-    const size_t got = fread(b->text + have, 1, MUL_BLOCK_BYTES - have, stdin);
+    while (have < MUL_BLOCK_BYTES) {
+      const ssize_t got = read(STDIN_FILENO, b->text + have, MUL_BLOCK_BYTES - have);
+      if (got < 0 && errno == EINTR) continue;
+      if (got <= 0) { /* EOF (or error): this is the last block */
+        more = false;
+        break;
+      }
+      have += (size_t)got;
+    }
     mp->us_read += now_us() - tr;
-    have += got;
-    if (have < MUL_BLOCK_BYTES) more = false; /* EOF (or error): this is the last block */
     size_t cut = have;
     if (more) { /* keep whole lines; a block without any newline is passed on as is (pieces of 1024 characters) */
       cut = mulfeed_cut(b->text, have);
@@ -564,13 +509,124 @@ static void cmd_mul(app *a) {
   mp->eof = true;
   pthread_cond_broadcast(&mp->cv);
   pthread_mutex_unlock(&a->mu);
-  for (int i = 0; i < n_parsers; ++i) pthread_join(parse_th[i], NULL);
-  for (int r = 0; r < a->n_gpus; ++r) pthread_join(rank_th[r], NULL);
   free(carry);
+  return NULL;
+}
+
+static void mul_start_feeder(app *a) { /* before open_devices: the text side runs while the GPUs come up */
+  static mul_pipe pipe;
+  mul_pipe *mp = &pipe;
+  mp->a = a, a->mul = mp;
+  pthread_cond_init(&mp->cv, NULL);
+  mp->n_parsers = (int)(a->threads_shown < 32 ? a->threads_shown : 32);
+  for (int i = 0; i < mp->n_parsers; ++i) pthread_create(&mp->parse_th[i], NULL, mul_parser_main, mp);
+  pthread_create(&mp->reader_th, NULL, mul_reader_main, mp);
+}
+
+/* next batch for a GPU: parsed blocks in sequence order until `room` keys are gathered. may_wait = false returns 0
+ * instead of sleeping when nothing is parsed yet (the caller has a submit in flight whose hits it can report first).
+ * *drained is set when the input is exhausted. */
+static uint32_t mul_gather(mul_pipe *mp, uint64_t (*keys)[4], uint32_t room, bool may_wait, bool *drained) {
+  app *a = mp->a;
+  uint32_t n = 0;
+  pthread_mutex_lock(&a->mu);
+  for (;;) {
+    mul_block *b = &mp->ring[mp->seq_take % MUL_RING];
+    const bool ready = mp->seq_take < mp->seq_read && b->state == 3;
+    if (ready) { /* a block of very short lines can hold more keys than one submit: take it in parts */
+      const uint32_t avail = b->count - mp->take_off, left = room - n, k = avail < left ? avail : left;
+      memcpy(keys + n, b->keys + mp->take_off, (size_t)k * sizeof *keys);
+      n += k, mp->take_off += k;
+      if (mp->take_off == b->count) {
+        b->state = 0, mp->take_off = 0;
+        mp->seq_take++;
+        pthread_cond_broadcast(&mp->cv);
+      }
+      if (n == room) break;
+      continue;
+    }
+    if (n || a->fatal) break; /* something to do (or giving up) */
+    if (mp->eof && mp->seq_take == mp->seq_read) {
+      *drained = true;
+      break;
+    }
+    if (!may_wait) break;
+    pthread_cond_wait(&mp->cv, &a->mu);
+  }
+  pthread_mutex_unlock(&a->mu);
+  return n;
+}
+
+static void *mul_rank_main(void *p) {
+  mul_pipe *mp = ((rank_arg *)p)->a->mul;
+  app *a = mp->a;
+  ecl_dev *dev = a->dev[((rank_arg *)p)->rank];
+  hit_buf hb = {0};
+  struct {
+    uint64_t (*keys)[4];
+    uint32_t n;
+    uint64_t t_submit;
+  } bt[ECL_MUL_DEPTH];
+  for (int i = 0; i < ECL_MUL_DEPTH; ++i)
+    if (!(bt[i].keys = malloc((size_t)MUL_BATCH_KEYS * sizeof *bt[i].keys))) die("out of memory");
+  int head = 0, inflight = 0;
+  bool drained = false;
+  while (!a->fatal) {
+    if (!drained && inflight < ECL_MUL_DEPTH) {
+      const int slot = (head + inflight) % ECL_MUL_DEPTH;
+      bt[slot].n = mul_gather(mp, bt[slot].keys, MUL_BATCH_KEYS, inflight == 0, &drained);
+      if (bt[slot].n) {
+        bt[slot].t_submit = now_us();
+        if (ecl_mul_submit(dev, (const uint64_t(*)[4])bt[slot].keys, bt[slot].n, a->flags & (ECL_A33 | ECL_A65)) != ECL_OK) {
+          fprintf(stderr, "ecloop: GPU error: %s\n", ecl_last_error(dev));
+          a->fatal = 1;
+          break;
+        }
+        inflight++;
+        if (inflight < ECL_MUL_DEPTH) continue; /* try to queue a second batch before waiting for the first */
+      }
+    }
+    if (!inflight) {
+      if (drained) break;
+      continue;
+    }
+    uint32_t nh = 0; /* oldest submit: hits -> found lines (check_found_mul, main.c:458-479: no verification here) */
+    if (collect_hits(a, dev, &hb, &nh) != 0) break;
+    const uint64_t t1 = now_us();
+    for (uint32_t i = 0; i < nh; ++i)
+      if (filter_exact(&a->filter, hb.hits[i].h160)) write_found(a, hb.hits[i].kind, hb.hits[i].h160, bt[head].keys[hb.hits[i].key_off]);
+    progress_add(a, bt[head].n);
+    pthread_mutex_lock(&a->mu);
+    mp->us_gpu += t1 - bt[head].t_submit, mp->us_report += now_us() - t1;
+    pthread_mutex_unlock(&a->mu);
+    head = (head + 1) % ECL_MUL_DEPTH, inflight--;
+  }
+  if (a->fatal) {
+    pthread_mutex_lock(&a->mu);
+    pthread_cond_broadcast(&mp->cv);
+    pthread_mutex_unlock(&a->mu);
+  }
+  for (int i = 0; i < ECL_MUL_DEPTH; ++i) free(bt[i].keys);
+  free(hb.hits), free(hb.pks), free(hb.xy), free(hb.h33), free(hb.h65);
+  return NULL;
+}
+
+static void cmd_mul(app *a) {
+  mul_pipe *mp = a->mul; /* reader and parsers have been running since setup() */
+  pthread_t rank_th[64];
+  rank_arg arg[64];
+  a->t_start = now_ms(); /* the clock of the status line starts when the devices are ready, like cmd_add */
+  for (int r = 0; r < a->n_gpus; ++r) {
+    arg[r].a = a, arg[r].rank = r;
+    pthread_create(&rank_th[r], NULL, mul_rank_main, &arg[r]);
+  }
+  pthread_join(mp->reader_th, NULL);
+  for (int i = 0; i < mp->n_parsers; ++i) pthread_join(mp->parse_th[i], NULL);
+  for (int r = 0; r < a->n_gpus; ++r) pthread_join(rank_th[r], NULL);
   if (a->fatal) exit(1);
   if (getenv("ECLOOP_VERBOSE"))
-    fprintf(stderr, "\nmul stages: read %.3f s, parse %.3f s (sum over %d threads), gpu submit+collect %.3f s, report %.3f s\n",
-            mp->us_read / 1e6, mp->us_parse / 1e6, n_parsers, mp->us_gpu / 1e6, mp->us_report / 1e6);
+    fprintf(stderr, "\nmul stages: read %.3f s, parse %.3f s (sum over %d threads), gpu submit..collect %.3f s (overlapping), report %.3f s\n",
+            mp->us_read / 1e6, mp->us_parse / 1e6, mp->n_parsers, mp->us_gpu / 1e6, mp->us_report / 1e6);
   finish(a);
 }
 
@@ -646,6 +702,63 @@ static uint32_t seed_from_text(const char *s) { /* encode_seed (lib/utils.c:108-
   return h;
 }
 
+typedef struct open_arg {
+  app *a;
+  int rank;
+  bool failed;
+  char msg[512];
+} open_arg;
+
+static void *open_one_device(void *p) {
+  open_arg *o = p;
+  if (ecl_open(&o->a->dev[o->rank], o->rank) != ECL_OK) {
+    o->failed = true; /* ecl_last_error(NULL) is one buffer for all threads: good enough for a message */
+    snprintf(o->msg, sizeof o->msg, "%s", ecl_last_error(NULL));
+  }
+  return NULL;
+}
+
+/* The `-f` filter goes to every GPU. List mode: a few KB, one ecl_set_filter each. `.blf` (blf_load, lib/utils.c:362-396):
+ * the file is never held in host memory; it is read in 64 MiB pieces into two pinned staging buffers and every piece
+ * is sent to all GPUs at once (asynchronous copies on each GPU's own PCIe link), so a multi-GB filter is resident
+ * everywhere after ONE pass over the file. ECLOOP_BLF_PEER=1 sends it to GPU 0 only and fans out over NVLink. */
+#define BLF_CHUNK_WORDS (8u << 20)
+static void load_filter_on_devices(app *a) {
+  ecl_filter *f = &a->filter;
+  if (f->bits) {
+    for (int r = 0; r < a->n_gpus; ++r)
+      if (ecl_set_filter(a->dev[r], f->bits, f->size) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+    return;
+  }
+  const uint64_t t0 = now_us();
+  const bool peer = getenv("ECLOOP_BLF_PEER") != NULL && a->n_gpus > 1;
+  const int direct = peer ? 1 : a->n_gpus;
+  uint64_t *buf[2] = {ecl_host_alloc((uint64_t)BLF_CHUNK_WORDS * 8), ecl_host_alloc((uint64_t)BLF_CHUNK_WORDS * 8)};
+  if (!buf[0] || !buf[1]) die("ecloop: cannot allocate pinned staging memory");
+  for (int r = 0; r < direct; ++r)
+    if (ecl_filter_alloc(a->dev[r], f->size) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+  uint64_t have = 0;
+  for (int c = 0; have < f->size; ++c) {
+    uint64_t *b = buf[c & 1];
+    if (c >= 2) /* the copies that read this buffer two pieces ago must have landed */
+      for (int r = 0; r < direct; ++r)
+        if (ecl_filter_flush(a->dev[r]) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+    const int64_t n = filter_stream_blf(f, b, BLF_CHUNK_WORDS, have);
+    if (n <= 0) exit(1);
+    for (int r = 0; r < direct; ++r)
+      if (ecl_filter_write(a->dev[r], have, b, (uint64_t)n) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+    have += (uint64_t)n;
+  }
+  for (int r = 0; r < direct; ++r)
+    if (ecl_filter_commit(a->dev[r]) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+  for (int r = direct; r < a->n_gpus; ++r)
+    if (ecl_filter_copy_peer(a->dev[r], a->dev[0]) != ECL_OK) die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
+  ecl_host_free(buf[0]), ecl_host_free(buf[1]);
+  if (getenv("ECLOOP_VERBOSE"))
+    fprintf(stderr, "filter: %.2f GiB resident on %d GPU(s) in %.2f s (%s)\n", (double)f->size * 8 / (1u << 30), a->n_gpus,
+            (double)(now_us() - t0) / 1e6, peer ? "GPU 0 + NVLink peer copies" : "one pass, all GPUs");
+}
+
 static void open_devices(app *a) {
   const int have = ecl_device_count();
   if (have <= 0) die("ecloop: no CUDA device found; this build has no CPU compute path (%s)", ecl_last_error(NULL));
@@ -657,17 +770,23 @@ static void open_devices(app *a) {
   if (want > have) want = have;
   if (want > 64) want = 64;
   a->dev = calloc((size_t)want, sizeof *a->dev);
-  for (int r = 0; r < want; ++r) {
-    if (ecl_open(&a->dev[r], r) != ECL_OK) die("ecloop: cannot open GPU %d: %s", r, ecl_last_error(NULL));
-    if (ecl_set_filter(a->dev[r], a->filter.bits, a->filter.size) != ECL_OK)
-      die("ecloop: GPU error: %s", ecl_last_error(a->dev[r]));
-  }
   a->n_gpus = want;
+  pthread_t th[64];
+  open_arg arg[64];
+  for (int r = 0; r < want; ++r) { /* contexts, window tables: every GPU at the same time */
+    arg[r].a = a, arg[r].rank = r, arg[r].failed = false;
+    pthread_create(&th[r], NULL, open_one_device, &arg[r]);
+  }
+  for (int r = 0; r < want; ++r) pthread_join(th[r], NULL);
+  for (int r = 0; r < want; ++r)
+    if (arg[r].failed) die("ecloop: cannot open GPU %d: %s", r, arg[r].msg);
+  load_filter_on_devices(a);
 }
 
 static void setup(app *a) { /* init (main.c:774-865) */
-  if (a->argc > 1) { /* the offline bloom tools come first, like main.c:776-778; they need no GPU */
-    if (!strcmp(a->argv[1], "blf-gen")) exit(blf_gen_main(a->argc, a->argv));
+  if (a->argc > 1) { /* the offline bloom tools come first, like main.c:776-778 */
+    if (!strcmp(a->argv[1], "blf-gen")) /* on the GPU when there is one (blfgpu.c); `-cpu` keeps the host loop */
+      exit(!opt_flag(a, "-cpu") && ecl_device_count() > 0 ? blf_gen_gpu_main(a->argc, a->argv) : blf_gen_main(a->argc, a->argv));
     if (!strcmp(a->argv[1], "blf-check")) exit(blf_check_main(a->argc, a->argv));
   }
   a->color = isatty(fileno(stdout));
@@ -713,6 +832,10 @@ static void setup(app *a) { /* init (main.c:774-865) */
 
   parse_range(a);
   parse_offs_size(a);
+  if (a->cmd == CMD_MUL) {
+    a->raw_text = opt_flag(a, "-raw");
+    mul_start_feeder(a);
+  }
   open_devices(a);
 
   printf("threads: %zu ~ addr33: %d ~ addr65: %d ~ endo: %d | filter: ", a->threads_shown, (a->flags & ECL_A33) != 0,
@@ -725,7 +848,6 @@ static void setup(app *a) { /* init (main.c:774-865) */
     printf("range_e: %016llx %016llx %016llx %016llx\n", (unsigned long long)a->range_e[3], (unsigned long long)a->range_e[2],
            (unsigned long long)a->range_e[1], (unsigned long long)a->range_e[0]);
   }
-  if (a->cmd == CMD_MUL) a->raw_text = opt_flag(a, "-raw");
   printf("----------------------------------------\n");
   fflush(stdout);
   if (getenv("ECLOOP_VERBOSE")) fprintf(stderr, "ecloop_b200: %d GPU(s), ABI %d\n", a->n_gpus, ecl_abi_version());

@@ -1,9 +1,12 @@
 /* filter.c — see filter.h */
 #include "filter.h"
 
+#include <errno.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #define BLOOM_MAGIC 0x45434246u /* "FBCE" on disk (lib/utils.c:274) */
 #define BLOOM_VERSION 1u
@@ -73,8 +76,52 @@ int filter_load_blf(ecl_filter *f, const char *path) {
     return -1;
   }
   fclose(fp);
-  f->bits = bits, f->size = size, f->list = NULL, f->count = 0;
+  f->bits = bits, f->size = size, f->list = NULL, f->count = 0, f->blf_fd = -1;
   return 0;
+}
+
+int filter_open_blf(ecl_filter *f, const char *path) {
+  memset(f, 0, sizeof *f);
+  f->blf_fd = -1;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    fprintf(stderr, "failed to open input file\n");
+    return -1;
+  }
+  struct {
+    uint32_t magic, version;
+    uint64_t size;
+  } head;
+  if (read(fd, &head, sizeof head) != (ssize_t)sizeof head) {
+    fprintf(stderr, "failed to read bloom filter header\n");
+    close(fd);
+    return -1;
+  }
+  if (head.magic != BLOOM_MAGIC || head.version != BLOOM_VERSION) {
+    fprintf(stderr, "invalid bloom filter version; create a new filter with blf-gen command\n");
+    close(fd);
+    return -1;
+  }
+#ifdef POSIX_FADV_SEQUENTIAL
+  posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+  f->size = head.size, f->blf_fd = fd;
+  return 0;
+}
+
+int64_t filter_stream_blf(ecl_filter *f, uint64_t *buf, uint64_t max_words, uint64_t already) {
+  const uint64_t want_words = f->size - already < max_words ? f->size - already : max_words;
+  size_t want = (size_t)want_words * 8, got = 0;
+  while (got < want) {
+    const ssize_t r = read(f->blf_fd, (char *)buf + got, want - got);
+    if (r < 0 && errno == EINTR) continue;
+    if (r <= 0) {
+      fprintf(stderr, "failed to read bloom filter bits\n");
+      return -1;
+    }
+    got += (size_t)r;
+  }
+  return (int64_t)want_words;
 }
 
 static int cmp_h160(const void *a, const void *b) {
@@ -101,6 +148,7 @@ static uint32_t hex8(const char *s) {
 
 int filter_load(ecl_filter *f, const char *path) {
   memset(f, 0, sizeof *f);
+  f->blf_fd = -1;
   if (!path) {
     fprintf(stderr, "missing filter file\n");
     return -1;
@@ -113,7 +161,7 @@ int filter_load(ecl_filter *f, const char *path) {
   const char *ext = strrchr(path, '.');
   if (ext && strcmp(ext, ".blf") == 0) {
     fclose(fp);
-    return filter_load_blf(f, path);
+    return filter_open_blf(f, path); /* streamed to the GPUs by the caller (ecloop.c load_filter_on_devices) */
   }
 
   /* Text list. The reference reads with fgets into a 41-byte buffer and keeps only reads of exactly 40
@@ -162,7 +210,9 @@ int filter_load(ecl_filter *f, const char *path) {
 void filter_free(ecl_filter *f) {
   free(f->bits);
   free(f->list);
+  if (f->blf_fd >= 0) close(f->blf_fd);
   memset(f, 0, sizeof *f);
+  f->blf_fd = -1;
 }
 
 bool filter_exact(const ecl_filter *f, const uint32_t h[5]) {

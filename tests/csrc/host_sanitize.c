@@ -44,8 +44,22 @@ int main(int argc, char **argv) {
   CHECK(filter_exact(&f, f.list[0].w) && bloom_has(f.bits, f.size, f.list[f.count - 1].w));
   CHECK(bloom_save(argv[2], f.bits, f.size) == 0);
   ecl_filter g;
-  CHECK(filter_load(&g, argv[2]) == 0); /* name ends in .blf */
+  CHECK(filter_load_blf(&g, argv[2]) == 0);
   CHECK(!g.list && g.size == f.size && memcmp(g.bits, f.bits, f.size * 8) == 0);
+  filter_free(&g);
+  CHECK(filter_load(&g, argv[2]) == 0); /* name ends in .blf: header only, words streamed in chunks */
+  CHECK(!g.list && !g.bits && g.size == f.size && g.blf_fd >= 0);
+  {
+    uint64_t *chunk = malloc(f.size * 8);
+    uint64_t have = 0;
+    while (have < g.size) {
+      const int64_t n = filter_stream_blf(&g, chunk + have, 5, have);
+      CHECK(n > 0);
+      have += (uint64_t)n;
+    }
+    CHECK(memcmp(chunk, f.bits, f.size * 8) == 0);
+    free(chunk);
+  }
   filter_free(&g);
   filter_free(&f);
   CHECK(filter_load(&f, "/nonexistent/x") == -1);

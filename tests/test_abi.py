@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", str(E.library_path())], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (ecl_[a-z0-9_]+)", out))
     assert set(syms) <= exported
-    assert lib.ecl_abi_version() == 1
+    assert lib.ecl_abi_version() == 2
 
 
 def test_is_sm100a_native():

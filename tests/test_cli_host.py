@@ -84,7 +84,8 @@ def test_sha256_host(hl):
 
 
 class Flt(C.Structure):
-    _fields_ = [("bits", C.POINTER(C.c_uint64)), ("size", C.c_uint64), ("list", C.POINTER(C.c_uint32 * 5)), ("count", C.c_size_t)]
+    _fields_ = [("bits", C.POINTER(C.c_uint64)), ("size", C.c_uint64), ("list", C.POINTER(C.c_uint32 * 5)), ("count", C.c_size_t),
+                ("blf_fd", C.c_int)]
 
 
 def test_filter_list_mode_matches_oracle(hl, tmp_path):
@@ -122,8 +123,26 @@ def test_blf_roundtrip(hl, tmp_path):
     raw = p.read_bytes()
     assert raw[:16] == struct.pack("<IIQ", 0x45434246, 1, 7) and len(raw) == 16 + 56  # lib/utils.c:274-360 layout
     f = Flt()
-    assert hl.filter_load(C.byref(f), str(p).encode()) == 0
+    assert hl.filter_load_blf(C.byref(f), str(p).encode()) == 0  # blf_load: whole file into host memory (blf-gen, blf-check)
     assert f.size == 7 and not f.list and [int(f.bits[i]) for i in range(7)] == list(bits)
+    hl.filter_free(C.byref(f))
+    # `-f x.blf`: header only, the words are streamed to the GPUs in chunks (here: 4 + 3 words)
+    assert hl.filter_load(C.byref(f), str(p).encode()) == 0
+    assert f.size == 7 and not f.list and not f.bits and f.blf_fd >= 0
+    hl.filter_stream_blf.restype = C.c_int64
+    buf = (C.c_uint64 * 4)()
+    got = []
+    while len(got) < 7:
+        n = hl.filter_stream_blf(C.byref(f), buf, C.c_uint64(4), C.c_uint64(len(got)))
+        assert n > 0
+        got += list(buf[:n])
+    assert got == list(bits)
+    hl.filter_free(C.byref(f))
+    short = tmp_path / "short.blf"
+    short.write_bytes(struct.pack("<IIQ", 0x45434246, 1, 9) + b"\0" * 8)
+    assert hl.filter_load(C.byref(f), str(short).encode()) == 0
+    assert hl.filter_stream_blf(C.byref(f), (C.c_uint64 * 16)(), C.c_uint64(16), C.c_uint64(0)) == -1  # "failed to read bloom filter bits"
+    hl.filter_free(C.byref(f))
     bad = tmp_path / "bad.blf"
     bad.write_bytes(struct.pack("<IIQ", 0x45434246, 2, 1) + b"\0" * 8)
     assert hl.filter_load(C.byref(f), str(bad).encode()) == -1
