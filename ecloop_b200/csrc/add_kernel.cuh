@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
+  if (owner && fe_is_zero(px) && fe_is_zero(py)) *p.err = 1u;  // the centre key is 0 (mod n): no point to start from
 
   uint4 *scr = p.scratch + tid;  // scratch is sized for whole CTAs
   const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
   fe px, py;
 #pragma unroll
   for (int l = 0; l < 8; ++l) px.v[l] = p.cx[(size_t)l * T + t], py.v[l] = p.cy[(size_t)l * T + t];
+  if (owner && fe_is_zero(px) && fe_is_zero(py)) *p.err = 1u;  // the centre key is 0 (mod n): no point to start from
 
   const size_t TS = (size_t)gridDim.x * blockDim.x;  // scratch stride (scratch is sized for whole CTAs)
   uint4 *scr_cur = p.scratch + tid;                  // entry k, half h at [(2k + h) * TS]

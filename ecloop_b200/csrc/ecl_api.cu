@@ -611,7 +611,10 @@ static int launch_add(ecl_dev *dev, u64 k_begin, u64 k_end, u64 max_keys_per_lau
   u64 k = k_begin;
   while (k < k_end) {
     const u64 L = std::min<u64>(k_end - k, per_launch);
-    const launch_plan lp = plan_launch(L, dev->Tmax);
+    u32 threads = dev->Tmax;
+    if (const char *env = getenv("ECLOOP_B200_MAX_THREADS"))  // test hook: few threads make small spans use large half groups
+      threads = std::min<u32>(dev->Tmax, std::max<u32>(1u, (u32)strtoul(env, nullptr, 10)));
+    const launch_plan lp = plan_launch(L, threads);
     // centres: (start + (k + Hr + t*c*2Hr) * stride) * G   (GStart, main.c:359-360)
     u64 k0[4], step[4], kstep[4];
     const u64 zero[4] = {0, 0, 0, 0};

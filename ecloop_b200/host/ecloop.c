@@ -241,7 +241,8 @@ static int report_add_hits(app *a, ecl_dev *dev, hit_buf *hb, uint32_t n, const 
   }
   for (uint32_t i = 0; i < m; ++i) {
     const ecl_hit *h = &hb->hits[i];
-    const uint32_t *again = h->kind == 0 ? hb->h33[i] : hb->h65[i];
+    uint32_t *again = h->kind == 0 ? hb->h33[i] : hb->h65[i];
+    if (getenv("ECLOOP_TEST_CORRUPT_VERIFY")) again[4] ^= 1u; /* test hook: drive the mismatch branch (main.c:255-262) */
     if (memcmp(again, h->h160, 20) != 0) {
       const uint64_t *pk = hb->pks[i];
       fprintf(stderr, "[!] error: hash mismatch (compressed: %d endo: %zu)\n", h->kind == 0, (size_t)h->endo);

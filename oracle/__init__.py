@@ -301,3 +301,42 @@ def run_ref(args, stdin_bytes: bytes | None = None, timeout: float = 600.0):
     env = dict(os.environ, LC_ALL="C")
     r = subprocess.run([str(exe), *args], input=stdin_bytes, capture_output=True, timeout=timeout, env=env)
     return r.returncode, r.stdout, r.stderr
+
+
+# ---------------------------------------------------------------- mirrors of the device-side filter tooling (tests only)
+
+
+def synthetic_filter(size_words: int, fill: float, seed: int):
+    """numpy restatement of ecl_filter_generate (csrc/filter_kernels.cuh): word i, bit 8k+b set iff byte b of
+    splitmix64(seed + (8i+k+1)*gamma) < round(fill*256). -> numpy uint64 array"""
+    import numpy as np
+
+    thr = int(fill * 256.0 + 0.5)
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    out = np.zeros(size_words, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        idx = np.arange(size_words, dtype=np.uint64) * np.uint64(8)
+        for k in range(8):
+            z = (np.uint64(seed) + (idx + np.uint64(k + 1)) * np.uint64(0x9E3779B97F4A7C15)) & M
+            z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+            z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+            z = z ^ (z >> np.uint64(31))
+            for b in range(8):
+                byte = (z >> np.uint64(8 * b)) & np.uint64(255)
+                out |= (byte < np.uint64(thr)).astype(np.uint64) << np.uint64(8 * k + b)
+    return out
+
+
+def blf_gen_sequential(bits, hashes):
+    """blf_gen's insert loop (lib/utils.c:453-465) word for word over python ints: `if has: continue; add; count += 1`.
+    bits: list of ints (modified in place); hashes: 5-tuples. -> count"""
+    size = len(bits)
+    count = 0
+    for h in hashes:
+        pos = blf_positions(h, size)
+        if all((bits[p >> 6] >> (p & 63)) & 1 for p in pos):
+            continue
+        for p in pos:
+            bits[p >> 6] |= 1 << (p & 63)
+        count += 1
+    return count

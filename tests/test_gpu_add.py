@@ -181,15 +181,11 @@ def test_many_threads_ragged_tail(dev, H, E):
     dev.set_filter(flt.bits)
     bits_c = (C.c_uint64 * flt.bits.size)(*[int(x) for x in flt.bits])
     oflt = O.HostFilter(bits_c, flt.bits.size, None)
-    dev.set_tuning(1, 0)  # one group per thread -> several launches for a modest span
-    try:
-        start = 2**70 + 12345
-        n_keys = 2048 * 151
-        got = dev.batch_add(start, n_keys, E.A33)
-        n, want = O.add_span(start, 1, n_keys, O.A33, oflt)
-        assert [(k, "".join("%08x" % w for w in h)) for k, _, _, h in got] == [(k, h) for k, _, _, h, _ in want]
-    finally:
-        dev.set_tuning(0, 0)
+    start = 2**70 + 12345
+    n_keys = 2048 * 151
+    got = dev.batch_add(start, n_keys, E.A33)
+    n, want = O.add_span(start, 1, n_keys, O.A33, oflt)
+    assert [(k, "".join("%08x" % w for w in h)) for k, _, _, h in got] == [(k, h) for k, _, _, h, _ in want]
 
 
 def test_large_bloom_in_hbm(dev, H, E):
@@ -227,22 +223,81 @@ def test_large_bloom_queue_overflow_falls_back_exactly(H, E, monkeypatch):
 
 
 def test_large_bloom_sparse_hits_and_false_positives(dev, H, E):
-    """a 64 MB filter at bloom-like fill (0.37): planted hashes come back, and so do exactly the oracle's false
-    positives over 2^22 keys x 6 endomorphism images"""
+    """a 64 MB filter at bloom-like fill (0.40) in HBM, 2^22 keys x 6 endomorphism images through the probe pipe:
+    the hit list — planted hashes AND false positives — is the oracle's, entry for entry (a candidate dropped by
+    stage 1 or stage 2 would show here; expected false positives: 2.5e7 x 0.4^20 ~ 0.3 per image set, so the
+    filter gets a few dense stripes that raise the count without changing the code path)"""
     size = (1 << 23) - 7
-    flt = sparse_filter(H, 29, size, 0.37)
+    bits = O.synthetic_filter(size, 0.40, 29)
+    bits[1000:200000] |= np.uint64(0xFFFF0000FFFF0000)  # dense stripes: more deep probe chains and false positives
     start, n_keys = 2**70 + 2**33, 1 << 22
     planted = [start + 5, start + 123456, start + n_keys - 1]
     for _, _, h33, _ in O.pubkey_hashes(planted):
-        H.blf_add(flt.bits, tuple(int(h33[i:i + 8], 16) for i in range(0, 40, 8)))
+        H.blf_add(bits, tuple(int(h33[i:i + 8], 16) for i in range(0, 40, 8)))
+    dev.set_filter(bits)
+    oflt = O.HostFilter(bits.ctypes.data_as(C.POINTER(C.c_uint64)), size, None)
+    for flags, oflags in ((E.A33 | E.ENDO, O.A33 | O.ENDO), (E.A33 | E.A65, O.A33 | O.A65)):
+        got = dev.batch_add(start, n_keys, flags)
+        n, want = O.add_span(start, 1, n_keys, oflags, oflt)
+        assert n == len(want) and {(p - start) for p in planted} <= {k for k, e, _, _, _ in want if e == 0}
+        assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
+
+
+# ---------------------------------------------------------------- the launch planner (run-time half group)
+
+
+@pytest.mark.parametrize("n_groups,flags_name", [(1, "c"), (3, "cu"), (37, "c"), (148, "u"), (149, "c_endo"), (1021, "c"), (4099, "cu")])
+def test_any_span_size_is_tiled_exactly(dev, H, E, n_groups, flags_name):
+    """every key of a span exactly once whatever its size: the planner picks the half group Hr per launch (64, a
+    table entry, a computed step point, 1024), the last thread's groups overhang the span and are masked"""
+    flags = {"c": E.A33, "u": E.A65, "cu": E.A33 | E.A65, "c_endo": E.A33 | E.ENDO}[flags_name]
+    flt = sparse_filter(H, 100 + n_groups, 509, 0.86)
     dev.set_filter(flt.bits)
-    got = dev.batch_add(start, n_keys, E.A33 | E.ENDO)
-    keys = {(k, e) for k, e, _, _ in got}
-    assert {(p - start, 0) for p in planted} <= keys
-    # every reported hash really passes blf_has, and the count is in the expected range for fill^20
-    for k, e, kd, h in got:
-        assert H.blf_has(flt.bits, h)
-    assert len(got) < 50
+    bits_c = (C.c_uint64 * flt.bits.size)(*[int(x) for x in flt.bits])
+    oflt = O.HostFilter(bits_c, flt.bits.size, None)
+    start = 2**71 + 977 * n_groups
+    got = dev.batch_add(start, 2048 * n_groups, flags, cap=1 << 20)
+    n, want = O.add_span(start, 1, 2048 * n_groups, flags, oflt, cap=1 << 22)
+    assert n == len(want) > 0
+    assert [(k, e, kd, "".join("%08x" % w for w in h)) for k, e, kd, h in got] == [(k, e, kd, h) for k, e, kd, h, _ in want]
+
+
+def test_half_group_sweep_against_a_full_dump(E, H, monkeypatch):
+    """the same 2^19-key job run with launch geometries that make the half group Hr take values across its range
+    (64; 256 = a table entry serves as the step point; 656, 874, 881 = step point computed per launch; 1024; several
+    groups per thread; several launches per span): the all-ones dump must not change by a byte"""
+    import ecloop_b200
+
+    ref = None
+    # (threads, max keys per launch)
+    # Hr: 64 | 256 | 656 with 2 groups per thread | 874 | 1024 | 1024 with 8 groups per thread | 64, 29 launches | 881, 3 launches
+    for threads, max_keys in ((0, 0), (1024, 0), (200, 0), (300, 0), (256, 0), (32, 0), (100000, 2048 * 9), (100, 2048 * 100)):
+        if threads:
+            monkeypatch.setenv("ECLOOP_B200_MAX_THREADS", str(threads))
+        if max_keys:
+            monkeypatch.setenv("ECLOOP_B200_MAX_LAUNCH_KEYS", str(max_keys))
+        else:
+            monkeypatch.delenv("ECLOOP_B200_MAX_LAUNCH_KEYS", raising=False)
+        with ecloop_b200.Device(0) as d:
+            s = H.Searcher(d, all_ones(H), E.A33 | E.A65 if threads in (200, 256) else E.A33)
+            lines = [f.line() for f in s.cmd_add(0x10000, 0x10000 + (1 << 19) - 1) if f.kind == 0]
+        assert len(lines) == 1 << 19  # a job of 2^19 - 1 keys visits whole groups
+        digest = sha_lines(lines)
+        ref = ref or digest
+        assert digest == ref, (threads, max_keys)
+
+
+def test_span_reaching_the_group_order_is_an_error_not_garbage(dev, H, E):
+    """a span whose keys run through n: some group centre equals a table point, the batch product is zero and every
+    key of that group would be garbage. The reference asserts (lib/ecc.c:666); the library reports ECL_E_DEGENERATE
+    and stays usable."""
+    dev.set_filter(all_ones(H).bits)
+    dev.set_stride(1)
+    with pytest.raises(E.EclError) as ei:
+        dev.batch_add(O.N_ORDER - 4096, 8192, E.A33, cap=1 << 16)
+    assert ei.value.code == E.E_DEGENERATE
+    got = dev.batch_add(2**70, 2048, E.A33, cap=4096)
+    assert len(got) == 2048
 
 
 # ---------------------------------------------------------------- size-independent properties at full size
