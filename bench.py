@@ -13,6 +13,13 @@ Prints ONE JSON line (rank 0). `value` is device-timed (CUDA events on the launc
 `e2e` is wall-clock through the public API with host buffers; `roofline` is the integer-ALU roofline the
 metric names (keys/s x 2700 canonical ALU ops) against the LOP3 issue rate measured in the same
 process, with the HBM view beside it; `cpu_baseline` times oracle/_ref on a bounded sample of the same range.
+
+After the timed headline the same line gets `secondary`: the other three BASELINE.json configs, each with its own
+device-timed value, end-to-end value, roofline and clocks (`--no-secondary` skips them):
+  mul_10M_cu     configs[2]: 10 M seeded keys per GPU through ecl_mul_submit from host buffers, -a cu
+  add_endo_blf   configs[3]: 6 GiB filter (Bernoulli(0.37), generated on the device, seed 4) in HBM, -endo, the range
+                 of Makefile:58 cut into one job-aligned shard per GPU
+  rnd_128_32_cu  configs[4]: `ecloop rnd -d 128:32 -a cu` — the C host on all GPUs of the run, consecutive 2^32 windows
 """
 from __future__ import annotations
 
@@ -51,8 +58,9 @@ def planted_offsets(n_steps: int, log2_step: int, per_rank: int = 8):
     return sorted(r.randrange(span) for _ in range(per_rank))
 
 
-def py_hash160_33(k: int) -> str:
-    """hash160 of the compressed public key of k: textbook double-and-add over python ints + hashlib"""
+def py_hash160(k: int):
+    """(hash160 of the compressed key, hash160 of the uncompressed key) of k: textbook double-and-add over python
+    ints + hashlib"""
     import hashlib
 
     p = 2**256 - 2**32 - 977
@@ -80,7 +88,13 @@ def py_hash160_33(k: int) -> str:
         base = add(base, base)
         k >>= 1
     ser = bytes([2 + (acc[1] & 1)]) + acc[0].to_bytes(32, "big")
-    return hashlib.new("ripemd160", hashlib.sha256(ser).digest()).hexdigest()
+    ser65 = b"\x04" + acc[0].to_bytes(32, "big") + acc[1].to_bytes(32, "big")
+    return (hashlib.new("ripemd160", hashlib.sha256(ser).digest()).hexdigest(),
+            hashlib.new("ripemd160", hashlib.sha256(ser65).digest()).hexdigest())
+
+
+def py_hash160_33(k: int) -> str:
+    return py_hash160(k)[0]
 
 
 class ClockSampler(threading.Thread):
@@ -199,6 +213,267 @@ def reference_arm(args):
     return 0
 
 
+
+# ---------------------------------------------------------------- secondary legs: BASELINE.json configs[2..4]
+
+CU_OPS_PER_KEY = 321 + 3 * 1384 + 2 * 950 + 2 * 12 + 2 * 42  # field + 3 SHA-256 blocks + 2 RIPEMD-160 blocks + serialise + probes
+ENDO_EXTRA_OPS = 2400  # each extra endomorphism image (hash160_33 + its share of the beta multiplications)
+RANGE71_S, RANGE71_E = 0x400000000000000000, 0x7FFFFFFFFFFFFFFFFF  # Makefile:58 (range_71)
+
+
+def _allreduce(world, local, vals, op):
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return list(vals)
+    t = torch.tensor(list(vals), device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+    return [float(x) for x in t.tolist()]
+
+
+def peaks_all(dev, peaks, world, local):
+    """rank 0 measured the pipe peaks; the legs only need them there"""
+    return peaks if peaks is not None else {"lop3_gops": 1.0}
+
+
+def leg_mul(E, H, dev, rank, world, local, peaks, n_keys, with_reference):
+    """configs[2]: `mul` on n_keys seeded random 256-bit keys per GPU, -a cu, keys in host memory (numpy), batches of
+    2^20 with ECL_MUL_DEPTH submits in flight; hits = every (n_keys/100)-th key, alternating encodings."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rng = np.random.default_rng(3 + rank)
+    keys = rng.integers(0, 2**64, size=(n_keys, 4), dtype=np.uint64)
+    keys[:, 3] &= np.uint64(0x7FFFFFFFFFFFFFFF)  # below n without a reduction step, like parsed hex keys
+    every = max(1, n_keys // 100)
+    planted = list(range(0, n_keys, every))
+    want = []
+    hashes = []
+    for j, i in enumerate(planted):
+        k = sum(int(keys[i, l]) << (64 * l) for l in range(4))
+        h33, h65 = py_hash160(k)
+        hashes.append(h33 if j % 2 == 0 else h65)
+        want.append((i, j % 2))
+    flt = H.filter_from_hashes(hashes)
+    dev.set_filter(np.ascontiguousarray(flt.bits, dtype=np.uint64))
+    lib, h = dev._lib, dev._h
+    batch = 1 << 20
+    import ctypes as C
+
+    def run_all():
+        found, hot, pend = [], 0.0, []
+        for b in range(0, n_keys, batch):
+            part = keys[b:b + batch]
+            dev._ck(lib.ecl_mul_submit(h, C.c_void_p(part.ctypes.data), part.shape[0], E.A33 | E.A65))
+            pend.append(b)
+            if len(pend) == E.MUL_DEPTH:
+                b0 = pend.pop(0)
+                hits, _ = dev.collect()
+                hot += dev.last_elapsed_ms()[1]
+                found += [(b0 + k, kd) for k, _, kd, hh in hits if flt.check_exact(hh)]
+        while pend:
+            b0 = pend.pop(0)
+            hits, _ = dev.collect()
+            hot += dev.last_elapsed_ms()[1]
+            found += [(b0 + k, kd) for k, _, kd, hh in hits if flt.check_exact(hh)]
+        return found, hot
+
+    run_all()  # warm-up (allocations, clocks)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    found, hot_ms = run_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop()
+    ok = sorted(found) == sorted(want)
+    wall_ms, hot_ms = _allreduce(world, local, [wall_ms, hot_ms], "MAX")
+    ok = _allreduce(world, local, [1.0 if ok else 0.0], "MIN")[0] == 1.0
+    if rank != 0:
+        return None, ok
+    kern = n_keys / (hot_ms * 1e-3) / 1e6  # per GPU (max rank)
+    e2e = n_keys * world / (wall_ms * 1e-3) / 1e6
+    B = max(1, -(-batch // (148 * 1024)))
+    field_mults = 15 * 11 + 7 + 270.0 / B
+    ops = field_mults * 45 + 15 * 8 * 16 + (CU_OPS_PER_KEY - 321)  # canonical ALU-pipe ops: 45 per multiplication (SURVEY App. C)
+    alu_peak = peaks["lop3_gops"] * 1e9
+    leg = {
+        "workload": f"mul: {n_keys} seeded 256-bit keys per GPU from host memory, -a cu (BASELINE configs[2]), batches of 2^20, {E.MUL_DEPTH} submits in flight",
+        "metric": "Mkeys/s (mul mode, -a cu)", "unit": "Mkeys/s", "n_gpus": world,
+        "value": round(kern * world, 2), "value_note": "mul_points_kernel + mul_hash_kernel, CUDA events on the launch stream, max over ranks, x n_gpus",
+        "e2e": {"value": round(e2e, 2), "unit": "Mkeys/s", "h2d_bytes_per_step": 32 * batch, "d2h_bytes_per_step": 4,
+                "note": "wall clock through ecl_mul_submit/ecl_collect from pageable host arrays, staging copy + H2D inside"},
+        "roofline": {"bound": "int_alu", "achieved": round(kern * 1e6 * ops / 1e12, 3), "peak": round(alu_peak / 1e12, 3), "unit": "Tops/s",
+                     "frac": round(kern * 1e6 * ops / alu_peak, 4),
+                     "model": f"{field_mults:.0f} field multiplications per key (15 mixed additions x 11, normalisation 7, inversion 270/{B}) x 45 canonical "
+                              f"ALU ops + 3 SHA-256 + 2 RIPEMD-160 blocks = {ops:.0f} ALU-pipe ops per key; IMAD.WIDE also occupies the ALU pipe on "
+                              "sm_100 (DESIGN.md), which this canonical count ignores"},
+        "parity_gate": "every planted key found, nothing else" if ok else "FAILED", "clocks": sampler.summary(),
+    }
+    if with_reference:
+        leg["reference"] = reference_mul_sample(min(n_keys, 1 << 20))
+    return leg, ok
+
+
+def reference_mul_sample(n):
+    """the unmodified reference's `mul -a cu -t nproc` on n seeded keys of the same distribution (bounded sample)"""
+    import numpy as np
+
+    import oracle as O
+
+    exe = O.ref_binary()
+    if exe is None:
+        return {"value": None, "note": "oracle/_ref not built"}
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    keys[:, 3] &= np.uint64(0x7FFFFFFFFFFFFFFF)
+    text = "".join("%016x%016x%016x%016x\n" % (int(k[3]), int(k[2]), int(k[1]), int(k[0])) for k in keys).encode()
+    cores = os.cpu_count() or 1
+    flt = ROOT / "tests" / "golden" / "btc-puzzles-hash"
+    t0 = time.perf_counter()
+    r = subprocess.run([str(exe), "mul", "-f", str(flt), "-a", "cu", "-t", str(cores), "-q", "-o", "/dev/null"], input=text, capture_output=True)
+    dt = time.perf_counter() - t0
+    status = [l for l in r.stderr.decode(errors="replace").replace("\r", "\n").splitlines() if "Mkeys/s ~" in l]
+    return {"value": round(n / dt / 1e6, 3), "unit": "Mkeys/s", "cores": cores, "kind": "reference",
+            "sample": f"{n} keys, mul -a cu -t {cores}, wall clock incl. its 0.4 s table build; status: {status[-1].strip() if status else ''}"}
+
+
+def leg_endo_blf(E, H, dev, rank, world, local, peaks, size_words, log2_step, steps):
+    """configs[3]: 6 GiB filter in HBM (fill 0.37, seed 4, + planted hashes through ecl_filter_add), `-endo`, addr33;
+    rank g sweeps the head of its job-aligned shard of 400000000000000000:7fffffffffffffffff (Makefile:58)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    total = RANGE71_E - RANGE71_S
+    per = total // world // (1 << 21) * (1 << 21)
+    shard = RANGE71_S + rank * per
+    step_keys = 1 << log2_step
+    r = __import__("random").Random(4 + rank)
+    planted = sorted(r.randrange((steps + 1) * step_keys) for _ in range(6))
+    t0 = time.perf_counter()
+    dev.filter_generate(size_words, 0.37, 4)
+    gen_s = time.perf_counter() - t0
+    new = dev.filter_add([tuple(int(py_hash160_33(shard + o)[i:i + 8], 16) for i in range(0, 40, 8)) for o in planted])
+    dev.filter_commit()
+    dev.set_stride(1)
+    flags = E.A33 | E.ENDO
+
+    def step(i):
+        hits = dev.batch_add(shard + i * step_keys, step_keys, flags)
+        return [(i * step_keys + k, e) for k, e, _, _ in hits]
+
+    step(0)  # warm-up: candidate queue allocation, clocks
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    hot_ms, hits = 0.0, []
+    for i in range(1, steps + 1):
+        hits += step(i)
+        hot_ms += dev.last_elapsed_ms()[1]
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop()
+    plain = {k for k, e in hits if e == 0}
+    ok = all(o in plain for o in planted if o >= step_keys)
+    n_hashes = 6 * steps * step_keys
+    expect_fp = n_hashes * dev.filter_fill() ** 20
+    wall_ms, hot_ms = _allreduce(world, local, [wall_ms, hot_ms], "MAX")
+    ok = _allreduce(world, local, [1.0 if ok else 0.0], "MIN")[0] == 1.0
+    n_hits = int(_allreduce(world, local, [float(len(hits))], "SUM")[0])
+    if rank != 0:
+        return None, ok
+    base = steps * step_keys / (hot_ms * 1e-3) / 1e6  # base keys per GPU (max rank)
+    e2e = steps * step_keys * world / (wall_ms * 1e-3) / 1e6
+    ops = ALU_OPS_PER_KEY + 5 * ENDO_EXTRA_OPS
+    alu_peak = peaks["lop3_gops"] * 1e9
+    pk, pk_src = measured_peaks()
+    probe_bytes = 6 * (1 + dev.filter_fill()) * 32  # stage 1 fetches two 16 B pieces (32 B sectors) per hash; ~fill^2 go on to stage 2
+    return {
+        "workload": f"add -endo addr33, {size_words * 8 / 2**30:.2f} GiB filter in HBM (Bernoulli(0.37), counter PRNG seed 4, generated on the device in {gen_s:.2f} s, "
+                    f"+{new} planted), range 400000000000000000:7fffffffffffffffff (Makefile:58) in {world} job-aligned shard(s) (BASELINE configs[3])",
+        "metric": "Mkeys/s counted (add -endo: 6 per base key, main.c:431)", "unit": "Mkeys/s", "n_gpus": world,
+        "value": round(6 * base * world, 2), "base_keys_value": round(base * world, 2),
+        "keys_per_step_per_gpu": step_keys, "steps": steps,
+        "e2e": {"value": round(6 * e2e, 2), "unit": "Mkeys/s", "h2d_bytes_per_step": 44, "d2h_bytes_per_step": 12 + 32 * (n_hits // max(1, steps * world))},
+        "roofline": {"bound": "int_alu", "achieved": round(base * 1e6 * ops / 1e12, 3), "peak": round(alu_peak / 1e12, 3), "unit": "Tops/s",
+                     "frac": round(base * 1e6 * ops / alu_peak, 4),
+                     "model": f"{ops} canonical ALU-pipe ops per base key (2700 + 5 x 2400, SURVEY 8d)",
+                     "hbm": {"achieved": round(base * 1e6 * probe_bytes / 1e9, 1), "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                             "frac": round(base * 1e6 * probe_bytes / 1e9 / pk.get("hbm_gbs", 6650.0), 4), "peak_source": pk_src,
+                             "model": f"{probe_bytes:.0f} B of random 32 B sectors per base key (6 hashes x 2 stage-1 probes)"}},
+        "false_positives": {"bloom_positive": n_hits, "planted": 6 * world, "expected_false": round(expect_fp * world, 1),
+                            "note": "bloom-only mode reports every bloom-positive hash; the same set is compared with the reference on a shared window in "
+                                    "tests/test_gpu_cli.py::test_gib_filter_endo_window_identical_to_reference and profiles/r02_config4_parity.txt"},
+        "parity_gate": "planted keys of the timed steps found" if ok else "FAILED", "clocks": sampler.summary(),
+    }, ok
+
+
+def leg_rnd(world, windows, with_reference):
+    """configs[4]: the drop-in binary `ecloop rnd -d 128:32 -a cu` on all GPUs of the run, `windows` consecutive 2^32
+    windows (ECLOOP_RND_WINDOWS stops it; the reference runs forever). Rank 0 only: the C host drives every GPU."""
+    exe = ROOT / "ecloop_b200" / "host" / "ecloop"
+    flt = ROOT / "tests" / "golden" / "btc-puzzles-hash"
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    r = subprocess.run([str(exe), "rnd", "-f", str(flt), "-d", "128:32", "-a", "cu", "-gpus", str(world)], capture_output=True,
+                       env=dict(os.environ, ECLOOP_RND_WINDOWS=str(windows), LC_ALL="C"))
+    wall = time.perf_counter() - t0
+    sampler.stop()
+    out = r.stdout.decode(errors="replace")
+    err = r.stderr.decode(errors="replace").replace("\r", "\n")
+    import re
+
+    per = [(int(a.replace(",", "")), float(b)) for a, b in re.findall(r"^\d[\d,]* / ([\d,]+) ~ ([\d.]+)s$", out, re.M)]
+    status = [l for l in err.splitlines() if "Mkeys/s ~" in l]
+    m = re.search(r"([\d.]+)s ~ ([\d.]+) Mkeys/s ~ [\d,]+ / ([\d,]+)", status[-1]) if status else None
+    ok = r.returncode == 0 and m is not None and len(per) == windows and all(c == 1 << 32 for c, _ in per)
+    leg = {
+        "workload": f"ecloop rnd -d 128:32 -a cu -gpus {world}: {windows} consecutive 2^32-key windows at stride 2^128 (BASELINE configs[4]), C host, "
+                    "each window split over the GPUs by the shared dispenser",
+        "metric": "Mkeys/s (rnd mode, -a cu, status line)", "unit": "Mkeys/s", "n_gpus": world,
+        "value": float(m.group(2)) if m else None, "value_note": "the binary's own status line: k_checked / elapsed since the devices were ready (main.c:137-139)",
+        "windows": len(per), "windows_per_s": round(len(per) / float(m.group(1)), 3) if m else None,
+        "e2e": {"value": round(windows * 2**32 / wall / 1e6, 2) if ok else None, "unit": "Mkeys/s",
+                "note": "process wall clock incl. start-up (CUDA contexts, window tables) / keys checked"},
+        "roofline": None,
+        "parity_gate": f"{windows} windows x 2^32 keys checked" if ok else f"FAILED rc={r.returncode}: {err[-200:]}",
+        "clocks": sampler.summary(),
+    }
+    if m and ok:
+        rate = float(m.group(2)) * 1e6 / world  # per GPU
+        leg["roofline"] = {"bound": "int_alu", "per_gpu_mkeys": round(rate / 1e6, 1), "ops_per_key": CU_OPS_PER_KEY,
+                           "model": "3 SHA-256 + 2 RIPEMD-160 blocks + field per key (SURVEY App. C figures; its table's 5034 omits one SHA block)"}
+    if with_reference:
+        leg["reference"] = reference_rnd_sample()
+    return leg, ok
+
+
+def reference_rnd_sample():
+    import oracle as O
+
+    exe = O.ref_binary()
+    if exe is None:
+        return {"value": None, "note": "oracle/_ref not built"}
+    cores = os.cpu_count() or 1
+    flt = ROOT / "tests" / "golden" / "btc-puzzles-hash"
+    lo = 0x8000000000000000000000000000000000000000000000000000000000000
+    args = [str(exe), "add", "-f", str(flt), "-r", "%x:%x" % (lo, lo + ((1 << 26) - 1 << 128)), "-d", "128:32", "-a", "cu", "-t", str(cores), "-q", "-o", "/dev/null"]
+    t0 = time.perf_counter()
+    r = subprocess.run(args, capture_output=True, env=dict(os.environ, LC_ALL="C"))
+    dt = time.perf_counter() - t0
+    status = [l for l in r.stderr.decode(errors="replace").replace("\r", "\n").splitlines() if "Mkeys/s ~" in l]
+    return {"value": round((1 << 26) / dt / 1e6, 3) if r.returncode == 0 else None, "unit": "Mkeys/s", "cores": cores, "kind": "reference",
+            "sample": f"add -d 128:32 -a cu over 2^26 keys at stride 2^128, -t {cores}, wall clock; status: {status[-1].strip() if status else ''}"}
+
+
 # ---------------------------------------------------------------- our arm
 
 
@@ -285,6 +560,26 @@ def ours_arm(args):
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         ok = bool(okt.item())
 
+    # ---- secondary legs (the other BASELINE configs), after the timed headline
+    secondary, sec_ok = {}, True
+    if not args.no_secondary:
+        with_ref = world == 1 and not args.no_cpu_baseline
+        leg, ok2 = leg_mul(E, H, dev, rank, world, local, peaks_all(dev, peaks, world, local), args.mul_keys, with_ref)
+        secondary["mul_10M_cu"], sec_ok = leg, sec_ok and ok2
+        leg, ok2 = leg_endo_blf(E, H, dev, rank, world, local, peaks_all(dev, peaks, world, local), int(args.blf_gib * 2**30) // 8 - 5,
+                                args.endo_log2_step, args.endo_steps)
+        secondary["add_endo_blf"], sec_ok = leg, sec_ok and ok2
+        dev.close()  # the C host of the rnd leg opens the GPUs itself
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            leg, ok2 = leg_rnd(world, args.rnd_windows, with_ref)
+            secondary["rnd_128_32_cu"], sec_ok = leg, sec_ok and ok2
+        if world > 1:
+            dist.barrier()
+    ok = ok and sec_ok
+
     if rank == 0:
         total_keys = args.steps * step_keys * world
         value = total_keys / (dev_ms * 1e-3) / 1e6
@@ -329,6 +624,8 @@ def ours_arm(args):
             "clocks": clocks,
             "found": found_total,
         }
+        if secondary:
+            line["secondary"] = secondary
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = 1 << 28 if cores >= 8 else 1 << 26
@@ -357,6 +654,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-keys-per-step", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the legs for BASELINE configs[2..4]")
+    ap.add_argument("--mul-keys", type=int, default=10_000_000)
+    ap.add_argument("--blf-gib", type=float, default=6.0)
+    ap.add_argument("--endo-log2-step", type=int, default=32)
+    ap.add_argument("--endo-steps", type=int, default=2)
+    ap.add_argument("--rnd-windows", type=int, default=50)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
