@@ -573,7 +573,7 @@ def ours_arm(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        if rank == 0:
+        if rank == 0 and args.rnd_windows > 0:
             leg, ok2 = leg_rnd(world, args.rnd_windows, with_ref)
             secondary["rnd_128_32_cu"], sec_ok = leg, sec_ok and ok2
         if world > 1:

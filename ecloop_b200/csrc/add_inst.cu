@@ -8,11 +8,31 @@
 // Which instances run the software-pipelined kernel (bit v = ADD_VARIANT v; only variants without the endomorphism
 // exist in that form), and which two-phase instances hash one point at a time (NW = 1: half the loop body).
 // The choice per variant is a measurement (profiles/r02_*_add_variants.txt), not a principle.
+// Round-2 measurements (profiles/r02_a_add_variants.txt, M base keys/s, filter in shared memory | 4 GiB filter in HBM):
+//   variant 2 (addr65)        two-phase NW=2 4077 | 3248   NW=1 4300 | 3956   pipelined 4411 | 3138
+//   variant 3 (both)          two-phase NW=2 2767 | 2206   NW=1 2976 | ....   pipelined 2888 | 1260
+//   variant 5 (addr33 + endo) two-phase NW=2 1300 | 1225   NW=1 1307 | ....
+//   variant 7 (both + endo)   two-phase NW=2  557 |  428   NW=1  561 | ....
+// A loop body beyond ~128 KB (NW=2 with two hash kinds, the pipelined form with both) streams its instructions from an
+// L2 that the random probe traffic keeps busy: with a filter in HBM the smaller body wins by up to 20 %.
+#if ADD_HBM
+#ifndef ECL_SP_MASK_HBM
+#define ECL_SP_MASK_HBM 0x02  // variant 1
+#endif
+#ifndef ECL_NW1_MASK_HBM
+#define ECL_NW1_MASK_HBM 0xEC  // variants 2, 3, 5, 6, 7
+#endif
+#define ECL_SP_MASK_ ECL_SP_MASK_HBM
+#define ECL_NW1_MASK_ ECL_NW1_MASK_HBM
+#else
 #ifndef ECL_SP_MASK
-#define ECL_SP_MASK 0x2  // variant 1 (addr33)
+#define ECL_SP_MASK 0x06  // variants 1 (addr33) and 2 (addr65)
 #endif
 #ifndef ECL_NW1_MASK
-#define ECL_NW1_MASK 0x0
+#define ECL_NW1_MASK 0xE8  // variants 3, 5, 6, 7
+#endif
+#define ECL_SP_MASK_ ECL_SP_MASK
+#define ECL_NW1_MASK_ ECL_NW1_MASK
 #endif
 
 #ifndef ADD_VARIANT
@@ -35,9 +55,9 @@
 #endif
 
 cudaError_t LAUNCH_NAME(const AddParams &p, unsigned grid, unsigned smem, cudaStream_t stream) {
-#if ((ECL_SP_MASK >> ADD_VARIANT) & 1) && !V_ENDO
+#if ((ECL_SP_MASK_ >> ADD_VARIANT) & 1) && !V_ENDO
   auto fn = add_kernel_sp<ADD_H, V_A33, V_A65, ADD_HBM != 0>;
-#elif (ECL_NW1_MASK >> ADD_VARIANT) & 1
+#elif (ECL_NW1_MASK_ >> ADD_VARIANT) & 1
   auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0, 1>;
 #else
   auto fn = add_kernel<ADD_H, V_A33, V_A65, V_ENDO, ADD_HBM != 0, 2>;

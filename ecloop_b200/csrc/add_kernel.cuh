@@ -58,7 +58,7 @@ __device__ __forceinline__ u32 group_keys_inside(const AddParams &p, u64 first_k
     __syncthreads();                                                                          \
   }                                                                                           \
   pipe_init(pipe, smem_raw + (SMEM_OFFSET_), &cand_count, p.bloom, p.cand);
-#define PROBE_PIPE_FINISH(HBM_) pipe_finish(pipe);
+#define PROBE_PIPE_FINISH(HBM_, SINGLE_) pipe_finish<SINGLE_>(pipe);
 
 template <bool HBM>
 struct PipeOf {
@@ -73,8 +73,12 @@ __device__ __forceinline__ void pipe_init(ProbePipe<ADD_THREADS> &pp, unsigned c
                                           const CandQueue &q) {
   pp.init(smem, cnt, bv, q);
 }
+template <bool SINGLE>
 __device__ __forceinline__ void pipe_finish(NoPipe &) {}
-__device__ __forceinline__ void pipe_finish(ProbePipe<ADD_THREADS> &pp) { pp.finish(); }
+template <bool SINGLE>
+__device__ __forceinline__ void pipe_finish(ProbePipe<ADD_THREADS> &pp) {
+  pp.template finish<SINGLE>();
+}
 
 // Thread t owns the consecutive groups [t*c, (t+1)*c) of 2*Hr keys. For one group with centre point
 // P = (start + (g*2Hr + Hr)*s)*G it forms every P +- (i+1)*s*G, i < Hr, sharing ONE field inversion through
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel(const 
       px = nx, py = ny;
     }
   }
-  PROBE_PIPE_FINISH(HBM)
+  PROBE_PIPE_FINISH(HBM, NW == 1)
 }
 
 // ---------------------------------------------------------------- K1-sp: the software-pipelined variant (no endomorphism)
@@ -378,5 +382,5 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     uint4 *sw = scr_cur;
     scr_cur = scr_nxt, scr_nxt = sw;
   }
-  PROBE_PIPE_FINISH(HBM)
+  PROBE_PIPE_FINISH(HBM, false)
 }

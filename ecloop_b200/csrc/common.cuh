@@ -97,14 +97,14 @@ __device__ __forceinline__ void probe_hash(NoPipe &, const BloomView &bv, const 
   if (bloom_has(bv, hh) && active) emit_hit(sink, off, hh, endo, kind);
 }
 
-// run-time slot (the pipe counts its submissions): for call sites that are executed for both points of a step
-__device__ __forceinline__ void probe_hash_rt(NoPipe &np, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
+// the single call site of an instance that hashes one point at a time (NW = 1)
+__device__ __forceinline__ void probe_hash_one(NoPipe &np, const BloomView &bv, const HitSink &sink, const u32 (&hh)[5], u64 off,
                                               u32 endo, u32 kind, bool active) {
   probe_hash<0>(np, bv, sink, hh, off, endo, kind, active);
 }
 
 template <int NW, bool A33, bool A65, bool ENDO, int SYNC = 0, class PIPE = NoPipe>
-__device__ __forceinline__ void check_points(  // with a ProbePipe: NW == 2 -> lane n uses slot n; NW == 1 -> run-time slot
+__device__ __forceinline__ void check_points(  // with a ProbePipe: NW == 2 -> lane n uses slot n; NW == 1 -> one slot, judged a hash later
     const BloomView &bv, const HitSink &sink, u32 (&x)[NW][8], u32 (&y)[NW][8],
                                              const u64 (&off)[NW], const bool (&active)[NW], PIPE &pipe) {
   constexpr int NE = ENDO ? 6 : 1;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void check_points(  // with a ProbePipe: NW == 2 -> l
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (NW == 1) probe_hash_rt(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
+        if (NW == 1) probe_hash_one(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
         else if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
         else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 0u, active[n]);
       }
@@ -148,7 +148,7 @@ __device__ __forceinline__ void check_points(  // with a ProbePipe: NW == 2 -> l
 #pragma unroll
       for (int n = 0; n < NW; ++n) {
         const u32 hh[5] = {h[0].l[n], h[1].l[n], h[2].l[n], h[3].l[n], h[4].l[n]};
-        if (NW == 1) probe_hash_rt(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
+        if (NW == 1) probe_hash_one(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
         else if (n & 1) probe_hash<1>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
         else probe_hash<0>(pipe, bv, sink, hh, off[n], (u32)e, 1u, active[n]);
       }

@@ -5,8 +5,7 @@
 // Replaces lib/ecc.c:546-929 of the reference (pe, _ec_jacobi_add1/_dbl1/_rdc1, ec_gtable_init/ec_gtable_mul)
 // and ctx_precompute_gpoints (main.c:219-246). The reference uses homogeneous projective coordinates and a
 // w=14 table; any correct algorithm gives the same canonical affine (x, y), so we use Jacobian coordinates
-// (a = 0 formulas) and w = 16 (16 windows, digits are the 16-bit halves of the 32-bit limbs, 67 MB table that
-// stays L2-resident on B200).
+// (a = 0 formulas) and a much wider window (W = 22 by default: 12 windows, a 2.95 GB table in HBM).
 #pragma once
 #include "fp.cuh"
 
@@ -18,10 +17,29 @@ struct jac {
   fe x, y, z;
 };
 
-#define GTAB_W 16
-#define GTAB_WINDOWS 16
-#define GTAB_PER_WIN 65535u
-#define GTAB_ENTRIES (GTAB_WINDOWS * GTAB_PER_WIN)  // 1,048,560 affine points of 64 B
+// Window width of the fixed-base table d * 2^(W w) * G. The reference uses W = 14 (lib/ecc.c:876: 19 windows, 30 MB);
+// with 180 GB of HBM the width is a pure trade of table bytes against additions per key:
+//   W = 16: 16 windows,  67 MB (L2-resident)      W = 22: 12 windows, 2.95 GB
+//   W = 24: 11 windows, 10.7 GB                   W = 26: 10 windows, 38.9 GB
+// One 64 B gather per window and key from a table far beyond L2 is cheap next to the ~2000 instructions of the
+// addition it feeds; the table is built on the device in tens of milliseconds (kernels.cuh gtab_fill).
+#ifndef GTAB_W
+#define GTAB_W 22
+#endif
+#define GTAB_WINDOWS ((256 + GTAB_W - 1) / GTAB_W)
+#define GTAB_TOP_BITS (256 - GTAB_W * (GTAB_WINDOWS - 1))  // bits of the top window
+#define GTAB_STRIDE (1u << GTAB_W)                          // slots per window: slot d - 1 holds d * 2^(W w) * G
+#define GTAB_ENTRIES ((size_t)(GTAB_WINDOWS - 1) * GTAB_STRIDE + ((size_t)1 << GTAB_TOP_BITS))
+#define GTAB_CHUNK 256u  // entries one thread of the table builder fills: (c*256 + k) * B = c*256*B + k*B
+static_assert(GTAB_W >= 9 && GTAB_W <= 28 && GTAB_TOP_BITS >= 8, "window width out of range");
+
+// digit w of the scalar k: bits [W w, W w + W)
+__device__ __forceinline__ u32 gtab_digit(const fe &k, int w) {
+  const int lo = w * GTAB_W, limb = lo >> 5, sh = lo & 31;
+  u32 v = k.v[limb] >> sh;
+  if (sh + GTAB_W > 32 && limb < 7) v |= k.v[limb + 1] << (32 - sh);
+  return v & ((1u << GTAB_W) - 1u);
+}
 
 __device__ __forceinline__ fe fe_dbl(const fe &a) { return fe_add(a, a); }
 
@@ -135,12 +153,15 @@ __device__ __forceinline__ void gtab_load(fe &x, fe &y, const uint4 *__restrict_
 // meets P = +-Q (DESIGN.md "degenerate cases").
 static __device__ __noinline__ bool gtab_mul(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
   bool have = false;
+  u32 dig[GTAB_WINDOWS];
+#pragma unroll
+  for (int w = 0; w < GTAB_WINDOWS; ++w) dig[w] = gtab_digit(k, w);
 #pragma unroll 1
   for (int w = 0; w < GTAB_WINDOWS; ++w) {
-    const u32 d = (k.v[w >> 1] >> ((w & 1) * 16)) & 0xffffu;
+    const u32 d = dig[w];
     if (d == 0) continue;
     fe qx, qy;
-    gtab_load(qx, qy, gtab, (u32)w * GTAB_PER_WIN + d - 1);
+    gtab_load(qx, qy, gtab, (u32)w * GTAB_STRIDE + d - 1);
     if (!have) {
       acc.x = qx, acc.y = qy, acc.z = fe_one();
       have = true;

@@ -196,9 +196,12 @@ extern "C" const char *ecl_last_error(const ecl_dev *dev) { return dev ? dev->er
 
 static int build_gtab(ecl_dev *dev) {
   CK(cudaMalloc(&dev->gtab, (size_t)GTAB_ENTRIES * 64));
-  CK(cudaMalloc(&dev->bases, GTAB_WINDOWS * 64));
+  CK(cudaMalloc(&dev->bases, (size_t)GTAB_WINDOWS * 64 + (size_t)GTAB_WINDOWS * GTAB_CHUNK * 64));
+  u32 *small = dev->bases + GTAB_WINDOWS * 16;  // k * B_w, k <= 256, behind the bases
   gtab_bases_kernel<<<1, 32, 0, dev->stream>>>(dev->bases);
-  gtab_fill_kernel<<<(GTAB_ENTRIES + 127) / 128, 128, 0, dev->stream>>>((u32 *)dev->gtab, dev->bases);
+  gtab_small_kernel<<<(GTAB_WINDOWS * GTAB_CHUNK + 127) / 128, 128, 0, dev->stream>>>(small, dev->bases);
+  const u32 chunks = (GTAB_WINDOWS - 1) * (GTAB_STRIDE / GTAB_CHUNK) + (1u << GTAB_TOP_BITS) / GTAB_CHUNK;
+  gtab_fill_kernel<<<(chunks + 127) / 128, 128, 0, dev->stream>>>(dev->gtab, (const uint4 *)small);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(dev->stream));
   return ECL_OK;

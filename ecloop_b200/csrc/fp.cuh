@@ -306,8 +306,138 @@ __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b) {
   return fp_reduce512(t);
 }
 
-// t = a^2: off-diagonal products once (28 IMAD.WIDE), doubled, plus the 8 squares.
-__device__ __forceinline__ fe fe_sqr(const fe &a) { return fe_mul(a, a); }
+// rows of 3, 2 and 1 products for the squaring (same conventions as fp_mad_row_c: aligned pairs, carry into the limb above)
+__device__ __forceinline__ void fp_mad_row3(u32 *acc, u32 a0, u32 a1, u32 a2, u32 b) {
+  asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+      "addc.u32       %6, %6, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+__device__ __forceinline__ void fp_mad_row2(u32 *acc, u32 a0, u32 a1, u32 b) {
+  asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32       %4, %4, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+      : "r"(a0), "r"(a1), "r"(b));
+}
+__device__ __forceinline__ void fp_mad_row1(u32 *acc, u32 a0, u32 b) {
+  asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32       %2, %2, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+      : "r"(a0), "r"(b));
+}
+
+// t[0..15] = a^2 (lib/ecc.c:349-444 computes each off-diagonal product once as well): the 28 products a[i]*a[j], i < j,
+// in 13 aligned rows (even columns in e, odd columns in o, like fp_mul_wide; a row's carry lands in a limb that
+// holds nothing but such carries until a later row covers it), then 2*(e + (o << 32)) + the 8 squares.
+// 36 IMAD.WIDE + 44 carry-chain adds instead of 64 + 31: IMAD.WIDE occupies an issue slot on BOTH integer pipes of
+// sm_100, so this is 15 ALU-pipe slots and 28 FMA-pipe slots less per squaring.
+__device__ __forceinline__ void fp_sqr_wide(u32 t[16], const fe &a) {
+  u32 e[16], o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) e[k] = 0, o[k] = 0;
+  fp_mad_row3(e + 2, a.v[2], a.v[4], a.v[6], a.v[0]);
+  fp_mad_row3(e + 4, a.v[3], a.v[5], a.v[7], a.v[1]);
+  fp_mad_row2(e + 6, a.v[4], a.v[6], a.v[2]);
+  fp_mad_row2(e + 8, a.v[5], a.v[7], a.v[3]);
+  fp_mad_row1(e + 10, a.v[6], a.v[4]);
+  fp_mad_row1(e + 12, a.v[7], a.v[5]);
+  fp_mad_row_c(o + 0, a.v[1], a.v[3], a.v[5], a.v[7], a.v[0]);
+  fp_mad_row3(o + 2, a.v[2], a.v[4], a.v[6], a.v[1]);
+  fp_mad_row3(o + 4, a.v[3], a.v[5], a.v[7], a.v[2]);
+  fp_mad_row2(o + 6, a.v[4], a.v[6], a.v[3]);
+  fp_mad_row2(o + 8, a.v[5], a.v[7], a.v[4]);
+  fp_mad_row1(o + 10, a.v[6], a.v[5]);
+  fp_mad_row1(o + 12, a.v[7], a.v[6]);
+  // m = e + (o << 32): limbs 0 and 1 of e are zero, so m[0] = 0, m[1] = o[0]
+  u32 m[16];
+  m[0] = 0, m[1] = o[0];
+  asm("add.cc.u32  %0, %14, %28;\n\t"
+      "addc.cc.u32 %1, %15, %29;\n\t"
+      "addc.cc.u32 %2, %16, %30;\n\t"
+      "addc.cc.u32 %3, %17, %31;\n\t"
+      "addc.cc.u32 %4, %18, %32;\n\t"
+      "addc.cc.u32 %5, %19, %33;\n\t"
+      "addc.cc.u32 %6, %20, %34;\n\t"
+      "addc.cc.u32 %7, %21, %35;\n\t"
+      "addc.cc.u32 %8, %22, %36;\n\t"
+      "addc.cc.u32 %9, %23, %37;\n\t"
+      "addc.cc.u32 %10, %24, %38;\n\t"
+      "addc.cc.u32 %11, %25, %39;\n\t"
+      "addc.cc.u32 %12, %26, %40;\n\t"
+      "addc.u32    %13, %27, %41;"
+      : "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7]), "=r"(m[8]), "=r"(m[9]), "=r"(m[10]), "=r"(m[11]),
+        "=r"(m[12]), "=r"(m[13]), "=r"(m[14]), "=r"(m[15])
+      : "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]),
+        "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]),
+        "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]));
+  // d = m + the squares a[i]^2 at limbs 2i, 2i+1 (one carry chain through all 8 products)
+  u32 d[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) d[k] = m[k];
+  asm("mad.lo.cc.u32  %0, %16, %16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+      "madc.hi.u32    %15, %23, %23, %15;"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(d[8]), "+r"(d[9]),
+        "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+  // t = d + m  (the second copy of the off-diagonal part); limb 0 of m is zero
+  t[0] = d[0];
+  asm("add.cc.u32  %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32    %14, %29, %44;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
+        "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+      : "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(d[8]), "r"(d[9]), "r"(d[10]), "r"(d[11]),
+        "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]),
+        "r"(m[8]), "r"(m[9]), "r"(m[10]), "r"(m[11]), "r"(m[12]), "r"(m[13]), "r"(m[14]), "r"(m[15]));
+}
+
+#ifndef ECL_FE_SQR_DEDICATED
+#define ECL_FE_SQR_DEDICATED 1  // 0: fe_sqr = fe_mul(a, a) (the round-1 form, kept for A/B timing of the big kernels)
+#endif
+__device__ __forceinline__ fe fe_sqr(const fe &a) {
+#if ECL_FE_SQR_DEDICATED
+  u32 t[16];
+  fp_sqr_wide(t, a);
+  return fp_reduce512(t);
+#else
+  return fe_mul(a, a);
+#endif
+}
 
 static __device__ __noinline__ fe fe_sqr_n(fe x, int n) {
 #pragma unroll 1

@@ -87,12 +87,15 @@ __device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_f
 // additions (8M + 3S). Returns false for k = 0 (mod n).
 static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
   int have = 0;
+  u32 dig[GTAB_WINDOWS];
+#pragma unroll
+  for (int w = 0; w < GTAB_WINDOWS; ++w) dig[w] = gtab_digit(k, w);
 #pragma unroll 1
   for (int w = 0; w < GTAB_WINDOWS; ++w) {
-    const u32 d = (k.v[w >> 1] >> ((w & 1) * 16)) & 0xffffu;
+    const u32 d = dig[w];
     if (d == 0) continue;
     fe qx, qy;
-    gtab_load(qx, qy, gtab, (u32)w * GTAB_PER_WIN + d - 1);
+    gtab_load(qx, qy, gtab, (u32)w * GTAB_STRIDE + d - 1);
     if (!have) {
       acc.x = qx, acc.y = qy, acc.z = fe_one();
       have = 1;
@@ -201,8 +204,12 @@ __global__ void __launch_bounds__(512, 1) mul_hash_kernel(const MulHashParams p)
 }
 
 // ---------------------------------------------------------------- window table build (one-off per device)
+// ec_gtable_init (lib/ecc.c:880-905) on the device, in three steps: the window bases B_w = 2^(W w) G, a small table
+// k * B_w (k <= 256) per window, and the fill: thread (w, c) owns the 256 entries (256 c + k) * B_w = S + k * B_w with
+// S = 256 c * B_w — 255 affine additions that share ONE inversion (Montgomery's trick, prefix products parked in the
+// x field of the entries they belong to). ~9 field multiplications per entry: 46 M entries (W = 22) take ~10 ms.
 
-// bases[w] = 2^(16 w) * G, affine (16 threads)
+// bases[w] = 2^(W w) * G, affine (one thread per window)
 __global__ void gtab_bases_kernel(u32 *bases) {
   const u32 w = threadIdx.x;
   if (w >= GTAB_WINDOWS) return;
@@ -222,35 +229,75 @@ __global__ void gtab_bases_kernel(u32 *bases) {
   for (int l = 0; l < 8; ++l) bases[w * 16 + l] = x.v[l], bases[w * 16 + 8 + l] = y.v[l];
 }
 
-// gtab[w*65535 + d-1] = d * bases[w], d = 1..65535, by left-to-right double-and-add, then normalised
-__global__ void __launch_bounds__(128) gtab_fill_kernel(u32 *gtab, const u32 *bases) {
-  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= GTAB_ENTRIES) return;
-  const u32 w = idx / GTAB_PER_WIN, d = idx % GTAB_PER_WIN + 1;
-  fe bx, by;
-  for (int l = 0; l < 8; ++l) bx.v[l] = bases[w * 16 + l], by.v[l] = bases[w * 16 + 8 + l];
+// m * (bx, by), m >= 1, by left-to-right double-and-add, affine result
+static __device__ __noinline__ void small_multiple(fe &x, fe &y, const fe &bx, const fe &by, u32 m) {
   jac a;
-  bool have = false;
-  for (int bit = GTAB_W - 1; bit >= 0; --bit) {
-    if (have) {
-      jac t;
-      jac_dbl(t, a);
+  a.x = bx, a.y = by, a.z = fe_one();
+  int bit = 31 - __clz(m);
+  for (--bit; bit >= 0; --bit) {
+    jac t;
+    jac_dbl(t, a);
+    a = t;
+    if ((m >> bit) & 1) {
+      jac_madd(t, a, bx, by);
       a = t;
     }
-    if ((d >> bit) & 1) {
-      if (!have) {
-        a.x = bx, a.y = by, a.z = fe_one();
-        have = true;
-      } else {
-        jac t;
-        jac_madd(t, a, bx, by);
-        a = t;
-      }
-    }
   }
-  fe x, y;
   jac_to_affine(x, y, a);
-  for (int l = 0; l < 8; ++l) gtab[(size_t)idx * 16 + l] = x.v[l], gtab[(size_t)idx * 16 + 8 + l] = y.v[l];
+}
+
+// small[w][k-1] = k * bases[w], k = 1..GTAB_CHUNK
+__global__ void __launch_bounds__(128) gtab_small_kernel(u32 *small, const u32 *bases) {
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= GTAB_WINDOWS * GTAB_CHUNK) return;
+  const u32 w = idx / GTAB_CHUNK, k = idx % GTAB_CHUNK + 1;
+  fe bx, by, x, y;
+  for (int l = 0; l < 8; ++l) bx.v[l] = bases[w * 16 + l], by.v[l] = bases[w * 16 + 8 + l];
+  small_multiple(x, y, bx, by, k);
+  for (int l = 0; l < 8; ++l) small[(size_t)idx * 16 + l] = x.v[l], small[(size_t)idx * 16 + 8 + l] = y.v[l];
+}
+
+__device__ __forceinline__ void st_point(uint4 *e, const fe &x, const fe &y) {
+  e[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]), e[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  e[2] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]), e[3] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+}
+
+// thread (w, c): entries d = 256 c + k, k < 256, of window w (slot w * GTAB_STRIDE + d - 1)
+__global__ void __launch_bounds__(128) gtab_fill_kernel(uint4 *gtab, const uint4 *small) {
+  const u32 full = GTAB_STRIDE / GTAB_CHUNK, top = (1u << GTAB_TOP_BITS) / GTAB_CHUNK;  // chunks per window
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (GTAB_WINDOWS - 1) * full + top) return;
+  const u32 w = idx / full < GTAB_WINDOWS - 1 ? idx / full : GTAB_WINDOWS - 1;
+  const u32 c = idx - w * full;
+  const uint4 *tk = small + (size_t)w * GTAB_CHUNK * 4;           // tk[(k-1)*4 ..] = k * B_w
+  uint4 *out = gtab + ((size_t)w * GTAB_STRIDE + (size_t)c * GTAB_CHUNK) * 4 - 4;  // out[k*4 ..] = slot of d = 256 c + k
+  if (c == 0) {
+    for (u32 k = 1; k < GTAB_CHUNK; ++k)
+      for (int q = 0; q < 4; ++q) out[k * 4 + q] = tk[(k - 1) * 4 + q];
+    return;
+  }
+  fe bx, by, sx, sy;  // S = c * (256 B_w)
+  bx = fe_from_u4(tk[(GTAB_CHUNK - 1) * 4 + 0], tk[(GTAB_CHUNK - 1) * 4 + 1]);
+  by = fe_from_u4(tk[(GTAB_CHUNK - 1) * 4 + 2], tk[(GTAB_CHUNK - 1) * 4 + 3]);
+  small_multiple(sx, sy, bx, by, c);
+  st_point(out, sx, sy);  // k = 0
+  fe acc = fe_one();
+  for (u32 k = 1; k < GTAB_CHUNK; ++k) {  // prefix products, parked in the x field of entry k
+    out[k * 4 + 0] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+    out[k * 4 + 1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+    acc = fe_mul_noinline(acc, fe_sub(fe_from_u4(tk[(k - 1) * 4 + 0], tk[(k - 1) * 4 + 1]), sx));
+  }
+  fe inv = fe_inv(acc);
+  for (u32 k = GTAB_CHUNK - 1; k >= 1; --k) {
+    const fe pre = fe_from_u4(out[k * 4 + 0], out[k * 4 + 1]);
+    const fe qx = fe_from_u4(tk[(k - 1) * 4 + 0], tk[(k - 1) * 4 + 1]), qy = fe_from_u4(tk[(k - 1) * 4 + 2], tk[(k - 1) * 4 + 3]);
+    const fe inv_k = fe_mul_noinline(inv, pre);
+    inv = fe_mul_noinline(inv, fe_sub(qx, sx));
+    const fe lam = fe_mul_noinline(fe_sub(qy, sy), inv_k);
+    const fe rx = fe_sub(fe_sub(fe_mul_noinline(lam, lam), sx), qx);
+    const fe ry = fe_sub(fe_mul_noinline(lam, fe_sub(sx, rx)), sy);
+    st_point(out + k * 4, rx, ry);
+  }
 }
 
 // ---------------------------------------------------------------- primitive parity kernels

@@ -95,11 +95,15 @@ struct ProbePipe {
   // hand one hash to the pipe; the verdict on the hash that used this slot before (PP_DEPTH submissions ago) is
   // taken first. Call sites alternate the slots 0, 1, 0, 1, ... with a compile-time SLOT, which keeps every
   // shared-memory address of the pipe in the form [register + immediate].
-  template <u32 slot>
+  // KEEP = younger groups that may still be in flight when this slot's previous occupant is judged: PP_DEPTH - 1 when
+  // the call sites alternate slots 0, 1 (two points hashed side by side, NW = 2); 0 when ONE call site serves every
+  // hash (NW = 1: the previous submission is a whole hash old, far longer than a DRAM access, so waiting for it is free
+  // and the single static slot keeps the address in the safe [R + imm] form).
+  template <u32 slot, int KEEP = PP_DEPTH - 1>
   __device__ __forceinline__ void submit(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
     static_assert(slot < PP_DEPTH, "slot out of range");
-    if (n >= PP_DEPTH) {
-      cp_async_wait<PP_DEPTH - 1>();
+    if (n >= (KEEP ? PP_DEPTH : 1u)) {
+      cp_async_wait<KEEP>();
       retire(slot);
     }
     const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
@@ -107,30 +111,6 @@ struct ProbePipe {
     const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
     cp_async_16(probe_s32 + (slot * 2 + 0) * THREADS * 16, bv.bits + (i0 & ~1ull), policy);
     cp_async_16(probe_s32 + (slot * 2 + 1) * THREADS * 16, bv.bits + (i1 & ~1ull), policy);
-    cp_async_commit();
-    const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
-    meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
-    meta[(slot * 2 + 1) * THREADS] =
-        make_uint4(h[4], (u32)off, (u32)(off >> 32), endo | (kind << 8) | ((active ? 1u : 0u) << 16) | (p0 << 17) | (p1 << 24));
-    ++n;
-  }
-
-  // Run-time slot WITH the L2 evict-first hint (two-phase instances that hash one point at a time, NW = 1): the slot's
-  // byte offset goes through an opaque move so that ptxas sees one plain vector register as the shared address
-  // (see cp_async_16: the [R+UR+imm] form it may pick otherwise is broken in CUDA 12.9).
-  __device__ __forceinline__ void submit_rt(const u32 h[5], u64 off, u32 endo, u32 kind, bool active) {
-    const u32 slot = n % PP_DEPTH;
-    if (n >= PP_DEPTH) {
-      cp_async_wait<PP_DEPTH - 1>();
-      retire(slot);
-    }
-    const u64 a0 = (u64)h[0] << 32 | h[1], a1 = (u64)h[2] << 32 | h[3], a2 = (u64)h[4] << 32 | h[0];
-    const u64 v0 = (a0 << 24) | (a1 >> 24), v1 = (a1 << 24) | (a2 >> 24);
-    const u64 i0 = bloom_word_index(v0 >> 6, bv.size, bv.magic), i1 = bloom_word_index(v1 >> 6, bv.size, bv.magic);
-    u32 dst = probe_s32 + slot * (2u * THREADS * 16u);
-    asm volatile("mov.b32 %0, %0;" : "+r"(dst));
-    cp_async_16(dst, bv.bits + (i0 & ~1ull), policy);
-    cp_async_16(dst + THREADS * 16u, bv.bits + (i1 & ~1ull), policy);
     cp_async_commit();
     const u32 p0 = ((u32)v0 & 63u) | (((u32)i0 & 1u) << 6), p1 = ((u32)v1 & 63u) | (((u32)i1 & 1u) << 6);
     meta[(slot * 2) * THREADS] = make_uint4(h[0], h[1], h[2], h[3]);
@@ -162,10 +142,15 @@ struct ProbePipe {
   }
 
   // end of the kernel: take the verdict on everything still in flight and publish the CTA's candidate count
+  template <bool SINGLE_SLOT = false>
   __device__ __forceinline__ void finish() {
     cp_async_wait<0>();
-    if (n >= 1) retire((n - 1) % PP_DEPTH);
-    if (n >= 2) retire((n - 2) % PP_DEPTH);
+    if (SINGLE_SLOT) {
+      if (n >= 1) retire(0);
+    } else {
+      if (n >= 1) retire((n - 1) % PP_DEPTH);
+      if (n >= 2) retire((n - 2) % PP_DEPTH);
+    }
     static_assert(PP_DEPTH == 2, "finish() retires exactly two slots");
     __syncthreads();
     if (threadIdx.x == 0) q.counts[blockIdx.x] = *cta_count;
@@ -179,9 +164,9 @@ __device__ __forceinline__ void probe_hash(ProbePipe<THREADS> &pipe, const Bloom
 }
 
 template <int THREADS>
-__device__ __forceinline__ void probe_hash_rt(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
-                                              u64 off, u32 endo, u32 kind, bool active) {
-  pipe.submit_rt(hh, off, endo, kind, active);
+__device__ __forceinline__ void probe_hash_one(ProbePipe<THREADS> &pipe, const BloomView &, const HitSink &, const u32 (&hh)[5],
+                                               u64 off, u32 endo, u32 kind, bool active) {
+  pipe.template submit<0, 0>(hh, off, endo, kind, active);
 }
 
 template <int THREADS>

@@ -45,6 +45,17 @@ def test_is_sm100a_native():
     assert "sm_100a" in out
 
 
+def test_probe_fetches_use_the_safe_address_form():
+    """ptxas 12.9 can emit LDGSTS [R+UR+imm] with an undefined uniform register for the probe pipe's cp.async
+    ("illegal instruction" at run time): every LDGSTS of the library must be in the [R(+imm)] form"""
+    import ecloop_b200 as E
+
+    out = subprocess.run(["cuobjdump", "-sass", str(E.library_path())], capture_output=True, text=True).stdout
+    ldgsts = [l for l in out.splitlines() if "LDGSTS" in l]
+    assert len(ldgsts) >= 12  # six HBM instances of the add kernel
+    assert not [l for l in ldgsts if re.search(r"\[R\d+\+UR", l)]
+
+
 def test_no_cpu_fallback():
     import ecloop_b200 as E
 

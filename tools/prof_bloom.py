@@ -5,7 +5,6 @@ import sys
 import time
 from pathlib import Path
 
-import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -15,17 +14,10 @@ lb = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 lk = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else (E.A33 | E.ENDO)
 words = (1 << lb) // 8 - 5  # not a power of two, like a real blf-gen size
-rng = np.random.default_rng(4)
-t0 = time.perf_counter()
-bits = np.zeros(words, dtype=np.uint64)
-chunk = 1 << 24
-for off in range(0, words, chunk):  # fill 0.37 ~ AND of ... : 3 random words: p(bit) = 1 - (1-0.5)^... use threshold on bytes instead
-    n = min(chunk, words - off)
-    b = rng.integers(0, 256, size=n * 64, dtype=np.uint8) < 95  # 95/256 = 0.371
-    bits[off:off + n] = np.packbits(b, bitorder="little").view(np.uint64)
-print(f"filter: {words * 8 / 2**30:.2f} GiB, fill {0.371:.3f}, built in {time.perf_counter() - t0:.1f} s", flush=True)
 with E.Device(0) as dev:
-    dev.set_filter(bits)
+    t0 = time.perf_counter()
+    dev.filter_generate(words, 0.37, 4)  # bits i.i.d. with p = 95/256, generated on the device
+    print(f"filter: {words * 8 / 2**30:.2f} GiB, fill {dev.filter_fill():.4f}, generated on the device in {time.perf_counter() - t0:.2f} s", flush=True)
     per_key = 6 if flags & E.ENDO else 1
     for i in range(3):
         hits = dev.batch_add(2**70 + (i << lk), 1 << lk, flags)

@@ -14,7 +14,12 @@ log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 r = random.Random(5)
 keys = E._fe_array([r.getrandbits(256) for _ in range(1 << log2)])
 flt = H.load_filter(ROOT / "tests" / "golden" / "btc-puzzles-hash")
+t_open = time.perf_counter()
 with E.Device(0) as dev:
+    print(f"ecl_open (context + window table build): {time.perf_counter() - t_open:.3f} s")
+    t_open = time.perf_counter()
+    E.Device(0).close()
+    print(f"second ecl_open in the same process (window table build + allocations only): {time.perf_counter() - t_open:.3f} s")
     dev.set_filter(flt.bits)
     for i in range(3):
         t0 = time.perf_counter()
