@@ -3,6 +3,27 @@
 // each with -DADD_HBM=0 (filter in shared memory, inline probes) and -DADD_HBM=1 (filter in HBM, probe pipe).
 #include <cuda_runtime.h>
 
+// Branch-free field arithmetic in the pipelined instances (fp.cuh fe_fix_branchfree): their point is that hash and field
+// work share basic blocks. The two-phase instances keep the branchy form (4 instructions instead of 17 per product).
+#ifndef ECL_FE_BRANCHFREE
+#if defined(ADD_HBM) && ADD_HBM
+#define ECL_FE_BRANCHFREE_WANT (((ECL_SP_BF_HBM_DEFAULT) >> ADD_VARIANT) & 1)
+#else
+#define ECL_FE_BRANCHFREE_WANT (((ECL_SP_BF_DEFAULT) >> ADD_VARIANT) & 1)
+#endif
+#ifndef ECL_SP_BF_DEFAULT
+#define ECL_SP_BF_DEFAULT 0x06
+#endif
+#ifndef ECL_SP_BF_HBM_DEFAULT
+#define ECL_SP_BF_HBM_DEFAULT 0x02
+#endif
+#if ECL_FE_BRANCHFREE_WANT
+#define ECL_FE_BRANCHFREE 1
+#else
+#define ECL_FE_BRANCHFREE 0
+#endif
+#endif
+
 #include "add_kernel.cuh"
 
 // Which instances run the software-pipelined kernel (bit v = ADD_VARIANT v; only variants without the endomorphism
@@ -20,7 +41,7 @@
 #define ECL_SP_MASK_HBM 0x02  // variant 1
 #endif
 #ifndef ECL_NW1_MASK_HBM
-#define ECL_NW1_MASK_HBM 0xEC  // variants 2, 3, 5, 6, 7
+#define ECL_NW1_MASK_HBM 0xCC  // variants 2, 3, 6, 7 (variant 5: NW=2 1225, NW=1 1181)
 #endif
 #define ECL_SP_MASK_ ECL_SP_MASK_HBM
 #define ECL_NW1_MASK_ ECL_NW1_MASK_HBM

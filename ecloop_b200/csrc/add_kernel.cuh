@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       inv = fe_mul(inv, fe_sub(gx, px));
     }
     fe ax, ay;  // the point waiting to be hashed
-    affine_add_inv(ax, ay, px, py, gx, fe_neg(gy), inv_i);
+    affine_add_inv(ax, ay, px, py, gx, fe_neg_nz(gy), inv_i);
     fe accn = fe_one();  // q'_k of the next group
 
     // ---- pass 2, pipelined
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
         gy = fe_from_u4(tab[(i - 1) * 4 + 2], tab[(i - 1) * 4 + 3]);
         inv_i = fe_mul(inv, q);
         inv = fe_mul(inv, fe_sub(gx, px));
-        affine_add_inv(ax, ay, px, py, gx, fe_neg(gy), inv_i);
+        affine_add_inv(ax, ay, px, py, gx, fe_neg_nz(gy), inv_i);
       }
       // the far end K+Hr (i == Hr-1) lies outside the group: computed along, never reported
       probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc + (u64)(i + 1), i != Hr - 1 && (u32)(Hr + (i + 1)) < inside);

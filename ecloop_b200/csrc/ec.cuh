@@ -5,7 +5,7 @@
 // Replaces lib/ecc.c:546-929 of the reference (pe, _ec_jacobi_add1/_dbl1/_rdc1, ec_gtable_init/ec_gtable_mul)
 // and ctx_precompute_gpoints (main.c:219-246). The reference uses homogeneous projective coordinates and a
 // w=14 table; any correct algorithm gives the same canonical affine (x, y), so we use Jacobian coordinates
-// (a = 0 formulas) and a much wider window (W = 22 by default: 12 windows, a 2.95 GB table in HBM).
+// (a = 0 formulas) and a much wider window (W = 24 by default: 11 windows, a 10.7 GB table in HBM).
 #pragma once
 #include "fp.cuh"
 
@@ -24,7 +24,7 @@ struct jac {
 // One 64 B gather per window and key from a table far beyond L2 is cheap next to the ~2000 instructions of the
 // addition it feeds; the table is built on the device in tens of milliseconds (kernels.cuh gtab_fill).
 #ifndef GTAB_W
-#define GTAB_W 22
+#define GTAB_W 24
 #endif
 #define GTAB_WINDOWS ((256 + GTAB_W - 1) / GTAB_W)
 #define GTAB_TOP_BITS (256 - GTAB_W * (GTAB_WINDOWS - 1))  // bits of the top window

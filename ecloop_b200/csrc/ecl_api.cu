@@ -207,6 +207,27 @@ static int build_gtab(ecl_dev *dev) {
   return ECL_OK;
 }
 
+static void free_mul_slot(mul_slot &s) {
+  cudaFreeHost(s.h_keys), cudaFreeHost(s.h_count), cudaFree(s.d_keys), cudaFree(s.d_scratch), cudaFree(s.d_hits), cudaFree(s.d_hit_count);
+  for (cudaEvent_t ev : {s.ev_begin, s.ev_k0, s.ev_k1, s.ev_end})
+    if (ev) cudaEventDestroy(ev);
+  s = mul_slot();
+}
+
+// The asynchronous probe wants a random 8-byte filter read to cost one 32 B sector of DRAM traffic, not a 128 B line.
+// The limit is device-wide, so it is only touched while a filter lives in HBM and put back afterwards.
+static void set_l2_granularity(ecl_dev *dev, bool want32) {
+  if (want32 && !dev->l2_gran_set) {
+    if (cudaDeviceGetLimit(&dev->l2_gran_saved, cudaLimitMaxL2FetchGranularity) != cudaSuccess) dev->l2_gran_saved = 64;
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    dev->l2_gran_set = true;
+  } else if (!want32 && dev->l2_gran_set) {
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, dev->l2_gran_saved);
+    dev->l2_gran_set = false;
+  }
+  cudaGetLastError();
+}
+
 extern "C" int ecl_open(ecl_dev **out, int ordinal) {
   if (!out) return fail(nullptr, ECL_E_ARG, "ecl_open: out is NULL");
   *out = nullptr;
@@ -225,6 +246,7 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
     dev->sm_count = prop.multiProcessorCount;
     dev->grid_max = (u32)dev->sm_count * ADD_MIN_BLOCKS;
     dev->Tmax = dev->grid_max * ADD_THREADS;
+    if (getenv("ECLOOP_B200_L2GRAN_AT_OPEN")) set_l2_granularity(dev, true);  // measurement hook (round-1 behaviour)
     CK(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
     dev->stream = dev->own_stream;
     CK(cudaStreamCreateWithFlags(&dev->io_stream, cudaStreamNonBlocking));
@@ -245,27 +267,6 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
   }
   *out = dev;
   return ECL_OK;
-}
-
-static void free_mul_slot(mul_slot &s) {
-  cudaFreeHost(s.h_keys), cudaFreeHost(s.h_count), cudaFree(s.d_keys), cudaFree(s.d_scratch), cudaFree(s.d_hits), cudaFree(s.d_hit_count);
-  for (cudaEvent_t ev : {s.ev_begin, s.ev_k0, s.ev_k1, s.ev_end})
-    if (ev) cudaEventDestroy(ev);
-  s = mul_slot();
-}
-
-// The asynchronous probe wants a random 8-byte filter read to cost one 32 B sector of DRAM traffic, not a 128 B line.
-// The limit is device-wide, so it is only touched while a filter lives in HBM and put back afterwards.
-static void set_l2_granularity(ecl_dev *dev, bool want32) {
-  if (want32 && !dev->l2_gran_set) {
-    if (cudaDeviceGetLimit(&dev->l2_gran_saved, cudaLimitMaxL2FetchGranularity) != cudaSuccess) dev->l2_gran_saved = 64;
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    dev->l2_gran_set = true;
-  } else if (!want32 && dev->l2_gran_set) {
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, dev->l2_gran_saved);
-    dev->l2_gran_set = false;
-  }
-  cudaGetLastError();
 }
 
 extern "C" void ecl_close(ecl_dev *dev) {
@@ -711,7 +712,7 @@ extern "C" int ecl_add_submit(ecl_dev *dev, const uint64_t start_pk[4], uint64_t
 
 typedef void (*mul_hash_fn)(const MulHashParams);
 #ifndef ECL_MUL_NW
-#define ECL_MUL_NW 2
+#define ECL_MUL_NW 1  // keys hashed side by side per thread in K2b: 1 is 1.5 % faster than 2 (profiles/r02_b_mul_variants.txt)
 #endif
 static mul_hash_fn pick_mul_hash(u32 flags) {
   const bool c = flags & ECL_A33, u = flags & ECL_A65;
@@ -745,9 +746,10 @@ static int ensure_mul_slot(ecl_dev *dev, mul_slot &s, u32 n) {
 
 // geometry of K2a for n keys: thread t owns keys m*T + t, m < B
 static void mul_geometry(const ecl_dev *dev, u32 n, u32 *T, u32 *B) {
-  // keys per thread: as many as it takes to keep ~1024 threads per SM busy, so that small batches still spread
-  // over the whole GPU and large ones amortise the per-thread inversion (270 multiplications)
-  const u32 want_threads = (u32)dev->sm_count * 1024u;
+  // keys per thread: as many as it takes to fill the threads that are resident at once (K2a: 2 CTAs of 256 per SM),
+  // so that small batches still spread over the whole GPU and large ones amortise the per-thread inversion
+  // (270 multiplications) and run as one wave
+  const u32 want_threads = (u32)dev->sm_count * 512u;
   u32 b = std::min<u32>(64u, (n + want_threads - 1) / want_threads);
   if (b == 0) b = 1;
   *B = b, *T = (n + b - 1) / b;

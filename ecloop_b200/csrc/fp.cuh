@@ -107,6 +107,32 @@ __device__ __forceinline__ void fe_canon(fe &a) {
   }
 }
 
+// Branch-free final correction of a product (ECL_FE_BRANCHFREE, used by the pipelined add kernel): r is the low 256 bits,
+// cy the carry out of the second fold. Both rare cases — cy = 1 (the value is 2^256 + r, r < 2^66) and r >= p — are
+// fixed by the same step, r += 2^32 + 977 (mod 2^256), applied under a mask instead of behind a branch: a branch ends the
+// basic block, and ptxas only interleaves the hash (ALU pipe) with the field arithmetic (FMA pipe) INSIDE a basic
+// block. 17 ALU-pipe instructions per product instead of ~4, paid for by the overlap.
+#ifndef ECL_FE_BRANCHFREE
+#define ECL_FE_BRANCHFREE 0
+#endif
+__device__ __forceinline__ void fe_fix_branchfree(fe &r, u32 cy) {
+  const u32 hi = r.v[7] & r.v[6] & r.v[5] & r.v[4] & r.v[3] & r.v[2];
+  const u64 lo = (u64)r.v[1] << 32 | r.v[0];
+  const u32 ge = (hi == 0xffffffffu) & (lo >= (((u64)FP_P1 << 32) | FP_P0));
+  const u32 m = 0u - (ge | cy);  // all ones: add 2^32 + 977
+  const u32 c0 = m & FP_C0, c1 = m & 1u;
+  asm("add.cc.u32  %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.cc.u32 %3, %3, 0;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.u32    %7, %7, 0;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+      : "r"(c0), "r"(c1));
+}
+
 // r = a + b (mod p), canonical inputs -> canonical output (the reference's fe_modp_add, lib/ecc.c:292-305,
 // only reduces on a 2^256 carry; on the hot path it is never used, we return the canonical residue).
 __device__ __forceinline__ fe fe_add(const fe &a, const fe &b) {
@@ -151,6 +177,22 @@ __device__ __forceinline__ fe fe_neg(const fe &a) {
       : "r"(p.v[0]), "r"(p.v[1]), "r"(p.v[2]), "r"(p.v[3]), "r"(p.v[4]), "r"(p.v[5]), "r"(p.v[6]), "r"(p.v[7]),
         "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
   if (fe_is_zero(a)) r = a;
+  return r;
+}
+
+// r = p - a for 0 < a < p (coordinates of curve points: y = 0 is not on the curve): no zero test
+__device__ __forceinline__ fe fe_neg_nz(const fe &a) {
+  fe r;
+  asm("sub.cc.u32  %0, %8, %9;\n\t"
+      "subc.cc.u32 %1, %10, %11;\n\t"
+      "subc.cc.u32 %2, -1, %12;\n\t"
+      "subc.cc.u32 %3, -1, %13;\n\t"
+      "subc.cc.u32 %4, -1, %14;\n\t"
+      "subc.cc.u32 %5, -1, %15;\n\t"
+      "subc.cc.u32 %6, -1, %16;\n\t"
+      "subc.u32    %7, -1, %17;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(FP_P0), "r"(a.v[0]), "r"(FP_P1), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
   return r;
 }
 
@@ -295,8 +337,12 @@ __device__ __forceinline__ fe fp_reduce512(const u32 t[16]) {
   const u32 r7 = r.v[7] + cy2;
   cy += (r7 < cy2);
   r.v[7] = r7;
+#if ECL_FE_BRANCHFREE
+  fe_fix_branchfree(r, cy);
+#else
   if (cy) fe_sub_p(r);  // value wrapped past 2^256 (prob ~2^-190): add 2^32+977; cannot carry again
   fe_canon(r);
+#endif
   return r;
 }
 

@@ -86,14 +86,17 @@ __device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_f
 // The first non-zero window is a load; the second is an affine + affine addition (4M + 2S); the rest are mixed
 // additions (8M + 3S). Returns false for k = 0 (mod n).
 static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
-  int have = 0;
+  int have = 0, dead = 0;  // dead: the sum hit infinity (k = 0 mod n); the loop still runs to its end (lockstep barriers)
   u32 dig[GTAB_WINDOWS];
 #pragma unroll
   for (int w = 0; w < GTAB_WINDOWS; ++w) dig[w] = gtab_digit(k, w);
 #pragma unroll 1
   for (int w = 0; w < GTAB_WINDOWS; ++w) {
+#if ECL_MULPTS_SYNC
+    __syncthreads();
+#endif
     const u32 d = dig[w];
-    if (d == 0) continue;
+    if (d == 0 || dead) continue;
     fe qx, qy;
     gtab_load(qx, qy, gtab, (u32)w * GTAB_STRIDE + d - 1);
     if (!have) {
@@ -114,15 +117,28 @@ static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const u
     const fe x3 = fe_sub(fe_sub(fe_sub(fe_sqr(rr), h3), v), v);
     const fe y3 = fe_sub(fe_mul(rr, fe_sub(v, x3)), fe_mul(acc.y, h3));
     const fe z3 = fe_mul(acc.z, h);
-    if (fe_is_zero(z3)) return false;  // k = n lands on -acc at the top window: infinity
+    if (fe_is_zero(z3)) dead = 1;  // k = n lands on -acc at the top window: infinity
     acc.x = x3, acc.y = y3, acc.z = z3;
   }
-  return have != 0;
+  return have != 0 && !dead;
 }
 
-__global__ void __launch_bounds__(256) mul_points_kernel(const MulParams p) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.T) return;
+#ifndef ECL_MULPTS_MINBLOCKS
+#define ECL_MULPTS_MINBLOCKS 2
+#endif
+#ifndef ECL_MULPTS_SYNC
+#define ECL_MULPTS_SYNC 0  // 1: the CTA walks the windows in lockstep (barrier per window) to share instruction fetches
+#endif
+__global__ void __launch_bounds__(256, ECL_MULPTS_MINBLOCKS) mul_points_kernel(const MulParams p) {
+  const u32 t0 = blockIdx.x * blockDim.x + threadIdx.x;
+#if ECL_MULPTS_SYNC
+  const u32 t = t0 < p.T ? t0 : p.T - 1;  // threads past the end run along on the last thread's keys and store nothing
+  const bool store = t0 < p.T;
+#else
+  if (t0 >= p.T) return;
+  const u32 t = t0;
+  const bool store = true;
+#endif
   const size_t T = p.T;
   uint4 *scr = p.scratch + t;
   fe acc = fe_one();
@@ -131,10 +147,14 @@ __global__ void __launch_bounds__(256) mul_points_kernel(const MulParams p) {
     const u32 j = m * p.T + t;
     jac a;
     bool ok = false;
+#if ECL_MULPTS_SYNC
+    ok = gtab_mul_fast(a, p.scalars[j < p.count ? j : p.count - 1], p.gtab) && j < p.count;
+#else
     if (j < p.count) ok = gtab_mul_fast(a, p.scalars[j], p.gtab);
+#endif
     if (!ok) a.x = fe_zero(), a.y = fe_zero(), a.z = fe_one();
     uint4 *slot = scr + (size_t)m * 8 * T;
-    st_fe(slot, T, a.x), st_fe(slot + 2 * T, T, a.y), st_fe(slot + 4 * T, T, a.z), st_fe(slot + 6 * T, T, acc);
+    if (store) st_fe(slot, T, a.x), st_fe(slot + 2 * T, T, a.y), st_fe(slot + 4 * T, T, a.z), st_fe(slot + 6 * T, T, acc);
     acc = fe_mul(acc, a.z);
   }
   fe inv = fe_inv(acc);
@@ -146,8 +166,8 @@ __global__ void __launch_bounds__(256) mul_points_kernel(const MulParams p) {
     inv = fe_mul(inv, z);
     const fe ax = ld_fe(slot, T), ay = ld_fe(slot + 2 * T, T);
     const fe zi2 = fe_sqr(zi);
-    st_fe(slot, T, fe_mul(ax, zi2));  // (0, 0) stays (0, 0): "no point for this key"
-    st_fe(slot + 2 * T, T, fe_mul(ay, fe_mul(zi2, zi)));
+    const fe fx = fe_mul(ax, zi2), fy = fe_mul(ay, fe_mul(zi2, zi));  // (0, 0) stays (0, 0): "no point for this key"
+    if (store) st_fe(slot, T, fx), st_fe(slot + 2 * T, T, fy);
   }
 }
 

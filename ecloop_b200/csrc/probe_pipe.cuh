@@ -179,7 +179,8 @@ __device__ __forceinline__ void probe_hash_dyn(NoPipe &np, const BloomView &bv, 
   probe_hash<0>(np, bv, sink, hh, off, endo, kind, active);
 }
 
-// stage 2: the full blf_has on every queued candidate. grid = (x, number of source CTAs)
+// stage 2: the rest of blf_has (probes 2..19, early exit) on every queued candidate: stage 1 saw probes 0 and 1 set.
+// grid = (x, number of source CTAs)
 static __global__ void __launch_bounds__(256) cand_verify_kernel(const CandQueue q, const BloomView bv, const HitSink sink) {
   const u32 src = blockIdx.y;
   u32 cnt = q.counts[src];
@@ -188,7 +189,7 @@ static __global__ void __launch_bounds__(256) cand_verify_kernel(const CandQueue
     const uint4 *e = q.entries + ((size_t)src * q.cap_per_cta + j) * 2;
     const uint4 a = e[0], b = e[1];
     const u32 hh[5] = {a.z, a.w, b.x, b.y, b.z};
-    if (bloom_has(bv, hh)) emit_hit(sink, (u64)a.x | (u64)a.y << 32, hh, b.w & 0xffu, (b.w >> 8) & 0xffu);
+    if (bloom_has_after_two(bv, hh)) emit_hit(sink, (u64)a.x | (u64)a.y << 32, hh, b.w & 0xffu, (b.w >> 8) & 0xffu);
   }
 }
 

@@ -38,7 +38,7 @@
 #include "u256.h"
 
 #define ECLOOP_VERSION "0.5.0"           /* the reference version this CLI mirrors (main.c:15) */
-#define MUL_BATCH_KEYS (1u << 20)       /* keys per ecl_mul_submit */
+#define MUL_BATCH_KEYS (1u << 22)       /* keys per ecl_mul_submit: 56 keys per GPU thread share one inversion */
 
 enum command { CMD_NONE, CMD_ADD, CMD_MUL, CMD_RND };
 
@@ -407,7 +407,7 @@ static void cmd_rnd(app *a) {
  * speed the text side is the bottleneck (10 M keys = 650 MB of hex), so the feeder is a three-stage pipeline:
  *   reader thread          read()s large blocks, cuts them at a line boundary, numbers them;
  *   parser threads (-t)    split a block into lines with the reference's rules and turn each into a key;
- *   rank threads (per GPU) take parsed blocks IN SEQUENCE ORDER, fuse them into submits of up to 2^20 keys and keep
+ *   rank threads (per GPU) take parsed blocks IN SEQUENCE ORDER, fuse them into submits of up to 2^22 keys and keep
  *                          TWO submits in flight (ECL_MUL_DEPTH): the upload and kernels of one batch run while the
  *                          previous batch's hits are reported and the next one is gathered.
  * Reader and parsers start BEFORE the GPUs are opened (setup), so context creation and the window-table build overlap
