@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "ecl_set_tuning", "ecl_prim_fp", "ecl_prim_scalar_mul", "ecl_prim_hash160", "ecl_prim_bloom", "ecl_peak_bench",
     "ecl_peak_bench_kind", "ecl_filter_alloc", "ecl_filter_write", "ecl_filter_flush", "ecl_filter_commit",
     "ecl_filter_read", "ecl_filter_copy_peer", "ecl_filter_add", "ecl_filter_generate", "ecl_filter_fill",
-    "ecl_host_alloc", "ecl_host_free",
+    "ecl_host_alloc", "ecl_host_free", "ecl_mul_reserve",
 )
 PEAK_KINDS = ("lop3", "iadd3", "shf", "imad", "imad_wide", "lop3+imad", "imad_const", "imad_hi", "lop3+imad_const",
               "shf+imad_wide", "lop3+imad_hi", "lop3x5+imad_constx3", "add2", "lop3+imad_wide", "shf+imad", "lop3+shf", "dfma", "dfma+lop3", "dfma+imad")
@@ -109,6 +109,7 @@ def load_library(rebuild: bool = False, experimental: bool = False) -> C.CDLL:
     lib.ecl_host_alloc.restype = C.c_void_p
     lib.ecl_host_free.argtypes = [C.c_void_p]
     lib.ecl_host_free.restype = None
+    lib.ecl_mul_reserve.argtypes = [C.c_void_p, C.c_uint32]
     if not experimental:
         _lib = lib
     return lib

@@ -294,11 +294,11 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     for (int k = 0; k < Hr; ++k) {
       scr_cur[(size_t)(2 * k) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
       scr_cur[(size_t)(2 * k + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
-      acc = fe_mul(acc, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), px));
+      acc = fe_mul_nc(acc, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), px));
     }
     scr_cur[(size_t)(2 * Hr) * TS] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
     scr_cur[(size_t)(2 * Hr + 1) * TS] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
-    tot = fe_mul(acc, fe_sub(sx, px));
+    tot = fe_mul_nc(acc, fe_sub(sx, px));
   }
 
 #pragma unroll 1
@@ -307,15 +307,15 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     const u32 inside = owner ? group_keys_inside(p, first) : 0u;
     const u64 kc = p.key_off0 + first + (u64)Hr;
 
-    if (inside && fe_is_zero(tot)) *p.err = 1u;
+    if (inside && fe_is_zero_modp(tot)) *p.err = 1u;
     fe inv = fe_inv(tot);  // 1 / (f_0 ... f_Hr)
 
     // ---- the group step first: next centre N = P + 2Hr*s*G
     fe nx, ny;
     {
       const fe qH = fe_from_u4(scr_cur[(size_t)(2 * Hr) * TS], scr_cur[(size_t)(2 * Hr + 1) * TS]);
-      const fe inv_s = fe_mul(inv, qH);  // 1 / f_Hr
-      inv = fe_mul(inv, fe_sub(sx, px));  // 1 / q_Hr
+      const fe inv_s = fe_mul_nc(inv, qH);  // 1 / f_Hr
+      inv = fe_mul_nc(inv, fe_sub(sx, px));  // 1 / q_Hr
       const fe sy = fe_from_u4(tab[H * 4 + 2], tab[H * 4 + 3]);
       affine_add_inv(nx, ny, px, py, sx, sy, inv_s);
     }
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     fe inv_i;
     {
       const fe q = fe_from_u4(scr_cur[(size_t)(2 * (Hr - 1)) * TS], scr_cur[(size_t)(2 * (Hr - 1) + 1) * TS]);
-      inv_i = fe_mul(inv, q);
-      inv = fe_mul(inv, fe_sub(gx, px));
+      inv_i = fe_mul_nc(inv, q);
+      inv = fe_mul_nc(inv, fe_sub(gx, px));
     }
     fe ax, ay;  // the point waiting to be hashed
     affine_add_inv(ax, ay, px, py, gx, fe_neg_nz(gy), inv_i);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
         const int k = Hr - 1 - i;
         scr_nxt[(size_t)(2 * k) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
         scr_nxt[(size_t)(2 * k + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
-        accn = fe_mul(accn, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), nx));
+        accn = fe_mul_nc(accn, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), nx));
       }
       probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc - (u64)(i + 1), (u32)(Hr - (i + 1)) < inside);
       // block Y: hash P + (i+1)G  ||  peel step i-1 and form P - iG
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
         const fe q = fe_from_u4(scr_cur[(size_t)(2 * (i - 1)) * TS], scr_cur[(size_t)(2 * (i - 1) + 1) * TS]);
         gx = fe_from_u4(tab[(i - 1) * 4 + 0], tab[(i - 1) * 4 + 1]);
         gy = fe_from_u4(tab[(i - 1) * 4 + 2], tab[(i - 1) * 4 + 3]);
-        inv_i = fe_mul(inv, q);
-        inv = fe_mul(inv, fe_sub(gx, px));
+        inv_i = fe_mul_nc(inv, q);
+        inv = fe_mul_nc(inv, fe_sub(gx, px));
         affine_add_inv(ax, ay, px, py, gx, fe_neg_nz(gy), inv_i);
       }
       // the far end K+Hr (i == Hr-1) lies outside the group: computed along, never reported
@@ -373,10 +373,10 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       check_one_slow<A33, A65>(bv, p.sink, bx, by, kc + 1, (u32)(Hr + 1) < inside);
       scr_nxt[(size_t)(2 * (Hr - 1)) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
       scr_nxt[(size_t)(2 * (Hr - 1) + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
-      accn = fe_mul(accn, fe_sub(fe_from_u4(tab[(Hr - 1) * 4 + 0], tab[(Hr - 1) * 4 + 1]), nx));
+      accn = fe_mul_nc(accn, fe_sub(fe_from_u4(tab[(Hr - 1) * 4 + 0], tab[(Hr - 1) * 4 + 1]), nx));
       scr_nxt[(size_t)(2 * Hr) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
       scr_nxt[(size_t)(2 * Hr + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
-      tot = fe_mul(accn, fe_sub(sx, nx));
+      tot = fe_mul_nc(accn, fe_sub(sx, nx));
     }
     px = nx, py = ny;
     uint4 *sw = scr_cur;

@@ -178,9 +178,10 @@ static __device__ __noinline__ bool gtab_mul(jac &acc, const fe &k, const uint4 
 
 // ---------------------------------------------------------------- affine addition with a shared inverse
 // (the body of batch_add, main.c:378-386): inv = 1/(qx - px)
+// inv may be any representative of the inverse below 2^256 (fe_mul_nc); px, py, qx, qy canonical; rx, ry canonical
 __device__ __forceinline__ void affine_add_inv(fe &rx, fe &ry, const fe &px, const fe &py, const fe &qx, const fe &qy,
                                                const fe &inv) {
-  const fe lam = fe_mul(fe_sub(qy, py), inv);
+  const fe lam = fe_mul_nc(fe_sub(qy, py), inv);  // only multiplied and squared below
   rx = fe_sub(fe_sub(fe_sqr(lam), px), qx);
   ry = fe_sub(fe_mul(lam, fe_sub(px, rx)), py);
 }

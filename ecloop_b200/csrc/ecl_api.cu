@@ -56,8 +56,6 @@ struct ecl_dev {
   u64 *bloom_bits = nullptr;
   u64 bloom_size = 0, bloom_magic = 0;
   double bloom_fill = 0.5;  // fraction of set bits (measured for filters that stay in HBM)
-  bool l2_gran_set = false;
-  size_t l2_gran_saved = 0;
 
   u32 Tmax = 0;
   u32 *centres = nullptr;  // 16 x Tmax u32 (SoA x then y)
@@ -214,20 +212,6 @@ static void free_mul_slot(mul_slot &s) {
   s = mul_slot();
 }
 
-// The asynchronous probe wants a random 8-byte filter read to cost one 32 B sector of DRAM traffic, not a 128 B line.
-// The limit is device-wide, so it is only touched while a filter lives in HBM and put back afterwards.
-static void set_l2_granularity(ecl_dev *dev, bool want32) {
-  if (want32 && !dev->l2_gran_set) {
-    if (cudaDeviceGetLimit(&dev->l2_gran_saved, cudaLimitMaxL2FetchGranularity) != cudaSuccess) dev->l2_gran_saved = 64;
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    dev->l2_gran_set = true;
-  } else if (!want32 && dev->l2_gran_set) {
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, dev->l2_gran_saved);
-    dev->l2_gran_set = false;
-  }
-  cudaGetLastError();
-}
-
 extern "C" int ecl_open(ecl_dev **out, int ordinal) {
   if (!out) return fail(nullptr, ECL_E_ARG, "ecl_open: out is NULL");
   *out = nullptr;
@@ -246,7 +230,6 @@ extern "C" int ecl_open(ecl_dev **out, int ordinal) {
     dev->sm_count = prop.multiProcessorCount;
     dev->grid_max = (u32)dev->sm_count * ADD_MIN_BLOCKS;
     dev->Tmax = dev->grid_max * ADD_THREADS;
-    if (getenv("ECLOOP_B200_L2GRAN_AT_OPEN")) set_l2_granularity(dev, true);  // measurement hook (round-1 behaviour)
     CK(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
     dev->stream = dev->own_stream;
     CK(cudaStreamCreateWithFlags(&dev->io_stream, cudaStreamNonBlocking));
@@ -273,7 +256,6 @@ extern "C" void ecl_close(ecl_dev *dev) {
   if (!dev) return;
   cudaSetDevice(dev->ordinal);
   cudaDeviceSynchronize();
-  set_l2_granularity(dev, false);
   cudaFree(dev->gtab), cudaFree(dev->bases), cudaFree(dev->add_table), cudaFree(dev->step_buf), cudaFree(dev->bloom_bits);
   cudaFree(dev->centres), cudaFree(dev->scratch), cudaFree(dev->d_hits), cudaFree(dev->d_hit_count);
   cudaFree(dev->cand_entries), cudaFree(dev->cand_counts);
@@ -331,7 +313,6 @@ static int filter_set_size(ecl_dev *dev, u64 size_words) {
 static int filter_measure(ecl_dev *dev) {
   dev->bloom_fill = 0.5;
   const bool in_hbm = dev->bloom_size * 8 > SMEM_FILTER_MAX;
-  set_l2_granularity(dev, in_hbm);
   if (in_hbm) {  // stays in HBM: measure its fill for the candidate-queue planner
     unsigned long long *d_total = nullptr, total = 0;
     CK(cudaMalloc(&d_total, sizeof total));
@@ -417,7 +398,6 @@ extern "C" int ecl_filter_copy_peer(ecl_dev *dev, ecl_dev *src) {
   CK(cudaMemcpyPeerAsync(dev->bloom_bits, dev->ordinal, src->bloom_bits, src->ordinal, (size_t)src->bloom_size * 8, dev->stream));
   CK(cudaStreamSynchronize(dev->stream));
   dev->bloom_fill = src->bloom_fill;
-  set_l2_granularity(dev, dev->bloom_size * 8 > SMEM_FILTER_MAX);
   return ECL_OK;
 }
 
@@ -753,6 +733,17 @@ static void mul_geometry(const ecl_dev *dev, u32 n, u32 *T, u32 *B) {
   u32 b = std::min<u32>(64u, (n + want_threads - 1) / want_threads);
   if (b == 0) b = 1;
   *B = b, *T = (n + b - 1) / b;
+}
+
+extern "C" int ecl_mul_reserve(ecl_dev *dev, uint32_t n) {
+  if (!dev || n == 0) return ECL_E_ARG;
+  if (dev->pending) return fail(dev, ECL_E_STATE, "ecl_mul_reserve with work pending");
+  CK(cudaSetDevice(dev->ordinal));
+  for (auto &s : dev->mslot) {
+    int rc = ensure_mul_slot(dev, s, n);
+    if (rc) return rc;
+  }
+  return ECL_OK;
 }
 
 // K2b over keys [begin, end) of a slot whose points are already affine

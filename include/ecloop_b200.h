@@ -86,6 +86,9 @@ int ecl_add_submit(ecl_dev *dev, const uint64_t start_pk[4], uint64_t n_keys, ui
  * submission order. */
 #define ECL_MUL_DEPTH 2
 int ecl_mul_submit(ecl_dev *dev, const uint64_t (*pks)[4], uint32_t n, uint32_t flags);
+/* optional: allocate the staging (pinned host + device) buffers of all ECL_MUL_DEPTH submit slots for batches of up to n
+ * keys now instead of inside the first submits (page-locking hundreds of MB takes tenths of a second) */
+int ecl_mul_reserve(ecl_dev *dev, uint32_t n);
 
 /* Wait for the submitted work and fetch its bloom-positive keys, sorted into the reference's `-t 1` emission
  * order: add -> by group of 2048, then plain before endo, then key, then endo index, then kind;
