@@ -150,6 +150,18 @@ def measured_traffic():
         return None, None
 
 
+def kernel_slot_census():
+    """the kernel's OWN ALU issue slots per key (SASS census of the hot loop + ncu's executed-instruction count), so that
+    the canonical-model fraction and the pipe fraction sit side by side"""
+    try:
+        d = json.loads((ROOT / "profiles" / "add_kernel_traffic.json").read_text())
+        c = d["loop_census"]
+        return {"alu_pipe_per_key": c["alu_pipe_per_key"], "imad_wide_per_key": c["imad_wide_per_key"],
+                "slots_per_key": c["alu_issue_slots_per_key"], "executed_thread_instructions_per_key_ncu": round(d.get("thread_instructions_per_key", 0), 1)}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -614,6 +626,9 @@ def ours_arm(args):
                 "traffic_note": (f"bytes per add_kernel launch of {int(per_launch_keys)} keys = {traffic_per_key:.2f} B/key DRAM read+write "
                                  f"measured by ncu ({traffic_src}); algorithmic bytes: {SCRATCH_BYTES_PER_KEY} B/key") if traffic_per_key else None,
                 "model": f"{ALU_OPS_PER_KEY} canonical ALU-pipe int32 ops per key (SURVEY 8d) x add_kernel keys/s (CUDA events around its launches)",
+                "alu_slots": (lambda c: None if not c else dict(c, frac_of_alu_issue_slots=round(hot_rate * c["slots_per_key"] / (alu_peak_tops * 1e12), 4),
+                                                                  note="the kernel's own ALU-pipe instructions + IMAD.WIDE (one slot on both integer pipes) per key, "
+                                                                       "hot loop only (tools/loop_census.py); its fraction of the measured LOP3 issue rate"))(kernel_slot_census()),
                 "peak_source": "measured in this process: LOP3.LUT issue rate over all SMs (ecl_peak_bench)",
                 "pipes": {k: round(v, 1) for k, v in peaks.items()},
                 "hbm": {"bound": "hbm", "achieved": round(hbm_achieved, 1), "peak": pk.get("hbm_gbs"), "unit": "GB/s",
