@@ -583,13 +583,15 @@ def ours_arm(args):
         secondary["add_endo_blf"], sec_ok = leg, sec_ok and ok2
         dev.close()  # the C host of the rnd leg opens the GPUs itself
         torch.cuda.synchronize()
+        # the other ranks wait on the CPU (gloo): an NCCL barrier is a kernel spinning on their GPUs, which the C host needs
+        cpu_group = dist.new_group(backend="gloo") if world > 1 else None
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
         if rank == 0 and args.rnd_windows > 0:
             leg, ok2 = leg_rnd(world, args.rnd_windows, with_ref)
             secondary["rnd_128_32_cu"], sec_ok = leg, sec_ok and ok2
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
     ok = ok and sec_ok
 
     if rank == 0:
