@@ -18,6 +18,7 @@ struct AddParams {
                           // so that T * groups_per_thread * 2*Hr tiles the launch's keys with (almost) no idle lanes
   u64 n_keys;             // keys of this launch; a key index (relative to the launch) >= n_keys is not reported
   u64 key_off0;           // index (in keys) of the first key of this launch inside the submitted span
+  u32 zero;               // 0, opaque to the compiler: the pinned form XORs (field result & zero) into the hash state
   u32 *err;               // set to 1 when a group's batch product is zero (a centre equal to +-m*s*G: the keys of the
                           // span reach 0 or n; the reference asserts there, lib/ecc.c:666)
   CandQueue cand;         // HBM kernels only: where stage 1 of the asynchronous probe queues its candidates
@@ -233,17 +234,104 @@ static __device__ __noinline__ void check_one_slow(const BloomView &bv, const Hi
 
 // the hash(es) of the point (ax, ay) inside a pipelined block: digest(s) out, probing is done by the caller after the
 // field work of the block so that the probe's branches do not cut the block in two
-template <bool A33, bool A65>
-__device__ __forceinline__ void hash_point(vw<1> (&h33)[5], vw<1> (&h65)[5], const fe &ax, const fe &ay) {
+// the hook (hash160.cuh) rides in the first hash of the point
+template <bool A33, bool A65, class HOOK>
+__device__ __forceinline__ void hash_point(vw<1> (&h33)[5], vw<1> (&h65)[5], const fe &ax, const fe &ay, HOOK &hook) {
   u32 xx[1][8], yy[1][8];
 #pragma unroll
   for (int l = 0; l < 8; ++l) xx[0][l] = ax.v[l], yy[0][l] = ay.v[l];
   if (A33) {
     const u32 odd[1] = {ay.v[0]};
-    hash160_33<1, 0>(h33, xx, odd);
+    hash160_33<1, 0, HOOK>(h33, xx, odd, hook);
   }
-  if (A65) hash160_65<1, 0>(h65, xx, yy);
+  if (A65) {
+    if (A33) hash160_65<1, 0>(h65, xx, yy);
+    else hash160_65<1, 0, HOOK>(h65, xx, yy, hook);
+  }
 }
+template <bool A33, bool A65>
+__device__ __forceinline__ void hash_point(vw<1> (&h33)[5], vw<1> (&h65)[5], const fe &ax, const fe &ay) {
+  NoHook none;
+  hash_point<A33, A65, NoHook>(h33, h65, ax, ay, none);
+}
+
+#ifndef ECL_SP_PINS
+#define ECL_SP_PINS 0  // 1: every field multiplication of a pass-2 step is pinned into the hash of its block (see HookX / HookY)
+#endif
+
+// Block X's field work as a hook: form P + (i+1)G from lam = (gy - py) * inv_i, and one prefix product of the next group.
+// Each piece runs where the hash calls the hook and XORs (result & zero) into a word of the hash state (zero is a kernel
+// parameter that is 0: ptxas cannot know), so the hash cannot pass that point before the piece is done and the scheduler
+// places the multiplication INSIDE the hash instead of behind it.
+struct HookX {
+  const fe &px, &py, &gx, &gy, &inv_i, &nx;
+  fe &bx, &by, &accn;
+  const uint4 *tab;
+  uint4 *scr_nxt;
+  size_t TS;
+  int k;
+  u32 zero;
+  fe lam;
+  __device__ __forceinline__ HookX(const fe &px_, const fe &py_, const fe &gx_, const fe &gy_, const fe &inv_i_, const fe &nx_, fe &bx_, fe &by_,
+                                   fe &accn_, const uint4 *tab_, uint4 *scr_, size_t TS_, int k_, u32 zero_)
+      : px(px_), py(py_), gx(gx_), gy(gy_), inv_i(inv_i_), nx(nx_), bx(bx_), by(by_), accn(accn_), tab(tab_), scr_nxt(scr_), TS(TS_), k(k_), zero(zero_) {}
+  __device__ __forceinline__ void sha(int i, u32 &w) {
+    if (i == 4) {
+      lam = fe_mul_nc(fe_sub(gy, py), inv_i);
+      w ^= lam.v[0] & zero;
+    }
+    if (i == 26) {
+      bx = fe_sub(fe_sub(fe_sqr(lam), px), gx);
+      w ^= bx.v[0] & zero;
+    }
+    if (i == 48) {
+      by = fe_sub(fe_mul(lam, fe_sub(px, bx)), py);
+      w ^= by.v[0] & zero;
+    }
+  }
+  __device__ __forceinline__ void rmd(int r, u32 &a) {
+    if (r == 1) {
+      scr_nxt[(size_t)(2 * k) * TS] = make_uint4(accn.v[0], accn.v[1], accn.v[2], accn.v[3]);
+      scr_nxt[(size_t)(2 * k + 1) * TS] = make_uint4(accn.v[4], accn.v[5], accn.v[6], accn.v[7]);
+      accn = fe_mul_nc(accn, fe_sub(fe_from_u4(tab[k * 4 + 0], tab[k * 4 + 1]), nx));
+      a ^= accn.v[0] & zero;
+    }
+  }
+};
+
+// Block Y's field work: peel the inverse of step i-1 (two independent products) and form P - iG.
+struct HookY {
+  const fe &px, &py, &gx, &gy, &q;
+  fe &inv, &inv_i, &ax, &ay;
+  u32 zero;
+  fe lam;
+  __device__ __forceinline__ HookY(const fe &px_, const fe &py_, const fe &gx_, const fe &gy_, const fe &q_, fe &inv_, fe &inv_i_, fe &ax_, fe &ay_, u32 zero_)
+      : px(px_), py(py_), gx(gx_), gy(gy_), q(q_), inv(inv_), inv_i(inv_i_), ax(ax_), ay(ay_), zero(zero_) {}
+  __device__ __forceinline__ void sha(int i, u32 &w) {
+    if (i == 2) {
+      inv_i = fe_mul_nc(inv, q);
+      w ^= inv_i.v[0] & zero;
+    }
+    if (i == 18) {
+      inv = fe_mul_nc(inv, fe_sub(gx, px));
+      w ^= inv.v[0] & zero;
+    }
+    if (i == 34) {
+      lam = fe_mul_nc(fe_sub(fe_neg_nz(gy), py), inv_i);
+      w ^= lam.v[0] & zero;
+    }
+    if (i == 52) {
+      ax = fe_sub(fe_sub(fe_sqr(lam), px), gx);
+      w ^= ax.v[0] & zero;
+    }
+  }
+  __device__ __forceinline__ void rmd(int r, u32 &a) {
+    if (r == 1) {
+      ay = fe_sub(fe_mul(lam, fe_sub(px, ax)), py);
+      a ^= ay.v[0] & zero;
+    }
+  }
+};
 template <bool A33, bool A65, class PIPE>
 __device__ __forceinline__ void probe_point(PIPE &pipe, const BloomView &bv, const HitSink &sink, const vw<1> (&h33)[5],
                                             const vw<1> (&h65)[5], u64 off, bool active) {
@@ -340,6 +428,25 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
 #pragma unroll 1
     for (int i = Hr - 1; i >= 1; --i) {
       if (ECL_HASH_SYNC) __syncthreads();
+#if ECL_SP_PINS
+      // block X / block Y with every field multiplication pinned into the block's hash (HookX / HookY above)
+      vw<1> h33[5], h65[5];
+      fe bx, by;
+      {
+        HookX hx(px, py, gx, gy, inv_i, nx, bx, by, accn, tab, scr_nxt, TS, Hr - 1 - i, p.zero);
+        hash_point<A33, A65, HookX>(h33, h65, ax, ay, hx);
+      }
+      probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc - (u64)(i + 1), (u32)(Hr - (i + 1)) < inside);
+      {
+        const fe q = fe_from_u4(scr_cur[(size_t)(2 * (i - 1)) * TS], scr_cur[(size_t)(2 * (i - 1) + 1) * TS]);
+        gx = fe_from_u4(tab[(i - 1) * 4 + 0], tab[(i - 1) * 4 + 1]);
+        gy = fe_from_u4(tab[(i - 1) * 4 + 2], tab[(i - 1) * 4 + 3]);
+        HookY hy(px, py, gx, gy, q, inv, inv_i, ax, ay, p.zero);
+        hash_point<A33, A65, HookY>(h33, h65, bx, by, hy);
+      }
+      probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc + (u64)(i + 1), i != Hr - 1 && (u32)(Hr + (i + 1)) < inside);
+    }
+#else
       // block X: hash P - (i+1)G  ||  form P + (i+1)G, and one pass-1 step of the next group
       vw<1> h33[5], h65[5];
       hash_point<A33, A65>(h33, h65, ax, ay);
@@ -365,6 +472,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
       // the far end K+Hr (i == Hr-1) lies outside the group: computed along, never reported
       probe_point<A33, A65>(pipe, bv, p.sink, h33, h65, kc + (u64)(i + 1), i != Hr - 1 && (u32)(Hr + (i + 1)) < inside);
     }
+#endif
     // ---- epilogue: step 0 (keys K-1 and K+1), the last two prefixes of the next group
     {
       fe bx, by;

@@ -118,6 +118,16 @@ __device__ __forceinline__ vw<N> vfadd(const vw<N> &a, u32 k) {
   return r;
 }
 
+// ---------------------------------------------------------------- scheduling hooks
+// A hook is called at fixed places inside a hash (before SHA-256 round i uses its message word; at the four round
+// boundaries of RIPEMD-160) with a reference to a live word of the hash state. The pipelined add kernel uses it to run
+// one field multiplication there and XOR (result & 0) into the word: a data dependency that costs one LOP3 and makes
+// ptxas place that multiplication inside the hash instead of after it (DESIGN.md K1 "pins"). NoHook compiles to nothing.
+struct NoHook {
+  __device__ __forceinline__ void sha(int, u32 &) {}
+  __device__ __forceinline__ void rmd(int, u32 &) {}
+};
+
 // ---------------------------------------------------------------- SHA-256 (FIPS 180-4; lib/sha256.c:399-453)
 
 // one compression; st = chaining value in/out, w = 16 message words (big-endian loads), clobbered
@@ -131,8 +141,8 @@ __device__ __forceinline__ void hash_sync_point() {
 
 // CMASK: bit i set = message word i is a compile-time constant (padding); additions with such words stay plain C
 // so that the compiler folds them, everything else is steered by the ECL_*_FMA levels above.
-template <int N, int SYNC = 0, u32 CMASK = 0>
-__device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
+template <int N, int SYNC = 0, u32 CMASK = 0, class HOOK = NoHook>
+__device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16], HOOK &hook, int hook_base = 0) {
   constexpr u32 K[64] = {
       0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
       0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
@@ -174,6 +184,7 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
       w[i & 15] = have ? r + kc : kc;
 #endif
     }
+    hook.sha(hook_base + i, w[i & 15].l[0]);
     const vw<N> S1 = vrotr(e, 6) ^ vrotr(e, 11) ^ vrotr(e, 25), ch = (e & f) ^ (~e & g);
     const vw<N> S0 = vrotr(a, 2) ^ vrotr(a, 13) ^ vrotr(a, 22), mj = (a & b) ^ (a & c) ^ (b & c);
 #if ECL_SHA_FMA == 0
@@ -196,6 +207,12 @@ __device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
   }
   st[0] = st[0] + a, st[1] = st[1] + b, st[2] = st[2] + c, st[3] = st[3] + d;
   st[4] = st[4] + e, st[5] = st[5] + f, st[6] = st[6] + g, st[7] = st[7] + h;
+}
+
+template <int N, int SYNC = 0, u32 CMASK = 0>
+__device__ __forceinline__ void sha256_compress(vw<N> st[8], vw<N> w[16]) {
+  NoHook none;
+  sha256_compress<N, SYNC, CMASK, NoHook>(st, w, none);
 }
 
 template <int N>
@@ -231,8 +248,8 @@ __device__ __forceinline__ void sha256_iv(vw<N> st[8]) {
 #endif
 
 // digest words of SHA-256 (sha[0..7], big-endian word values) -> h160_t words
-template <int N, int SYNC = 0>
-__device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) {
+template <int N, int SYNC = 0, class HOOK = NoHook>
+__device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8], HOOK &hook) {
   vw<N> w[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) w[i] = vbswap(sha[i]);  // digest bytes read back as little-endian words
@@ -243,8 +260,10 @@ __device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) 
   const u32 h0 = 0x67452301u, h1 = 0xefcdab89u, h2 = 0x98badcfeu, h3 = 0x10325476u, h4 = 0xc3d2e1f0u;
   vw<N> al = vset<N>(h0), bl = vset<N>(h1), cl = vset<N>(h2), dl = vset<N>(h3), el = vset<N>(h4);
   vw<N> ar = al, br = bl, cr = cl, dr = dl, er = el;
-#define RMD_ROUND_BOUNDARY \
-  if (SYNC > 1) hash_sync_point<SYNC>();
+  int rmd_boundary = 0;
+#define RMD_ROUND_BOUNDARY               \
+  if (SYNC > 1) hash_sync_point<SYNC>(); \
+  hook.rmd(rmd_boundary++, al.l[0]);
 #include "rmd160_steps.inc"
 #undef RMD_ROUND_BOUNDARY
   out[0] = vbswap(cl + dr + h1);
@@ -254,12 +273,18 @@ __device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) 
   out[4] = vbswap(bl + cr + h0);
 }
 
+template <int N, int SYNC = 0>
+__device__ __forceinline__ void rmd160_of_sha(vw<N> out[5], const vw<N> sha[8]) {
+  NoHook none;
+  rmd160_of_sha<N, SYNC, NoHook>(out, sha, none);
+}
+
 // ---------------------------------------------------------------- point -> hash160
 
 // X[i] = big-endian word i of the coordinate = limb 7-i (little-endian 32-bit limbs)
 // compressed key 02|03 || X (lib/addr.c:33-45): one block
-template <int N, int SYNC = 0>
-__device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y_odd)[N]) {
+template <int N, int SYNC, class HOOK>
+__device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y_odd)[N], HOOK &hook) {
   vw<N> w[16], st[8];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
@@ -272,14 +297,19 @@ __device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], c
   for (int i = 9; i < 15; ++i) w[i] = vset<N>(0);
   w[15] = vset<N>(33 * 8);
   sha256_iv(st);
-  sha256_compress<N, SYNC, 0xFE00u>(st, w);
+  sha256_compress<N, SYNC, 0xFE00u, HOOK>(st, w, hook);
   hash_sync_point<SYNC>();
-  rmd160_of_sha<N, SYNC>(out, st);
+  rmd160_of_sha<N, SYNC, HOOK>(out, st, hook);
+}
+template <int N, int SYNC = 0>
+__device__ __forceinline__ void hash160_33(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y_odd)[N]) {
+  NoHook none;
+  hash160_33<N, SYNC, NoHook>(out, x, y_odd, none);
 }
 
 // uncompressed key 04 || X || Y (lib/addr.c:47-67): two blocks
-template <int N, int SYNC = 0>
-__device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y)[N][8]) {
+template <int N, int SYNC, class HOOK>
+__device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y)[N][8], HOOK &hook) {
   vw<N> w[16], st[8];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
@@ -291,7 +321,7 @@ __device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], c
     for (int i = 9; i < 16; ++i) w[i].l[n] = __funnelshift_r(y[n][15 - i], y[n][16 - i], 8);
   }
   sha256_iv(st);
-  sha256_compress<N, SYNC>(st, w);
+  sha256_compress<N, SYNC, 0u, HOOK>(st, w, hook);  // the hook sees rounds 0..63 of the first block only
   hash_sync_point<SYNC>();
 #pragma unroll
   for (int n = 0; n < N; ++n) w[0].l[n] = (y[n][0] << 24) | 0x00800000u;
@@ -300,5 +330,10 @@ __device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], c
   w[15] = vset<N>(65 * 8);
   sha256_compress<N, SYNC, 0xFFFEu>(st, w);
   hash_sync_point<SYNC>();
-  rmd160_of_sha<N, SYNC>(out, st);
+  rmd160_of_sha<N, SYNC, HOOK>(out, st, hook);
+}
+template <int N, int SYNC = 0>
+__device__ __forceinline__ void hash160_65(vw<N> out[5], const u32 (&x)[N][8], const u32 (&y)[N][8]) {
+  NoHook none;
+  hash160_65<N, SYNC, NoHook>(out, x, y, none);
 }
