@@ -255,6 +255,9 @@ __device__ __forceinline__ void hash_point(vw<1> (&h33)[5], vw<1> (&h65)[5], con
   hash_point<A33, A65, NoHook>(h33, h65, ax, ay, none);
 }
 
+#ifndef ECL_SP_SYNC_EVERY
+#define ECL_SP_SYNC_EVERY 1  // lockstep barrier every n-th pass-2 step of the pipelined kernel
+#endif
 #ifndef ECL_SP_PINS
 #define ECL_SP_PINS 0  // 1: every field multiplication of a pass-2 step is pinned into the hash of its block (see HookX / HookY)
 #endif
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(ADD_THREADS, ADD_MIN_BLOCKS) add_kernel_sp(con
     // ---- pass 2, pipelined
 #pragma unroll 1
     for (int i = Hr - 1; i >= 1; --i) {
-      if (ECL_HASH_SYNC) __syncthreads();
+      if (ECL_HASH_SYNC && (i % ECL_SP_SYNC_EVERY) == 0) __syncthreads();
 #if ECL_SP_PINS
       // block X / block Y with every field multiplication pinned into the block's hash (HookX / HookY above)
       vw<1> h33[5], h65[5];

@@ -115,6 +115,12 @@ __device__ __forceinline__ void fe_canon(fe &a) {
 #ifndef ECL_FE_BRANCHFREE
 #define ECL_FE_BRANCHFREE 0
 #endif
+// ECL_FE_NC = 1: fe_mul_nc really skips the canonical correction (12 instructions less per such product). Measured
+// (r02_f): no gain on the addr33 instance with the filter in shared memory (6 566 vs 6 583 Mkeys/s) and -9 % on its HBM
+// twin (ptxas schedules the 7 000-instruction loop differently), so it is off; fe_mul_nc is then fe_mul.
+#ifndef ECL_FE_NC
+#define ECL_FE_NC 0
+#endif
 __device__ __forceinline__ void fe_fix_branchfree(fe &r, u32 cy) {
   const u32 hi = r.v[7] & r.v[6] & r.v[5] & r.v[4] & r.v[3] & r.v[2];
   const u64 lo = (u64)r.v[1] << 32 | r.v[0];
@@ -339,7 +345,7 @@ __device__ __forceinline__ fe fp_reduce512_t(const u32 t[16]) {
   cy += (r7 < cy2);
   r.v[7] = r7;
 #if ECL_FE_BRANCHFREE
-  if (FIX == 1) {  // only the wrap past 2^256 (then r < 2^66): the three low limbs take 2^32 + 977
+  if (FIX == 1 && ECL_FE_NC) {  // only the wrap past 2^256 (then r < 2^66): the three low limbs take 2^32 + 977
     const u32 c0 = (0u - cy) & FP_C0;
     asm("add.cc.u32  %0, %0, %3;\n\t"
         "addc.cc.u32 %1, %1, %4;\n\t"
