@@ -294,7 +294,8 @@ __device__ __forceinline__ void fp_mul_wide(u32 t[16], const fe &a, const fe &b)
 
 // t (512 bit) mod p, canonical. 2^256 = 2^32 + 977 (mod p): fold the high half twice (lib/ecc.c:331-346),
 // then the rare final corrections. Unlike ecc.c:341-344 the carry out of the second fold is honoured.
-template <int FIX>  // 0: canonical result (branchy or branch-free per ECL_FE_BRANCHFREE); 1: any representative < 2^256
+template <int FIX>  // 0: canonical result (branchy or branch-free per ECL_FE_BRANCHFREE); 1: any representative < 2^256;
+                    // 2: canonical, always branch-free (kernels that want independent products in one basic block)
 __device__ __forceinline__ fe fp_reduce512_t(const u32 t[16]) {
   // a[0..9] = lo + hi*977 + (hi << 32)
   u32 a[10], o[9];
@@ -344,21 +345,22 @@ __device__ __forceinline__ fe fp_reduce512_t(const u32 t[16]) {
   const u32 r7 = r.v[7] + cy2;
   cy += (r7 < cy2);
   r.v[7] = r7;
-#if ECL_FE_BRANCHFREE
-  if (FIX == 1 && ECL_FE_NC) {  // only the wrap past 2^256 (then r < 2^66): the three low limbs take 2^32 + 977
-    const u32 c0 = (0u - cy) & FP_C0;
-    asm("add.cc.u32  %0, %0, %3;\n\t"
-        "addc.cc.u32 %1, %1, %4;\n\t"
-        "addc.u32    %2, %2, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
-        : "r"(c0), "r"(cy));
+  constexpr bool branchfree = (FIX == 2) || ECL_FE_BRANCHFREE;
+  if (branchfree) {
+    if (FIX == 1 && ECL_FE_NC) {  // only the wrap past 2^256 (then r < 2^66): the three low limbs take 2^32 + 977
+      const u32 c0 = (0u - cy) & FP_C0;
+      asm("add.cc.u32  %0, %0, %3;\n\t"
+          "addc.cc.u32 %1, %1, %4;\n\t"
+          "addc.u32    %2, %2, 0;"
+          : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
+          : "r"(c0), "r"(cy));
+    } else {
+      fe_fix_branchfree(r, cy);
+    }
   } else {
-    fe_fix_branchfree(r, cy);
+    if (cy) fe_sub_p(r);  // value wrapped past 2^256 (prob ~2^-190): add 2^32+977; cannot carry again
+    fe_canon(r);
   }
-#else
-  if (cy) fe_sub_p(r);  // value wrapped past 2^256 (prob ~2^-190): add 2^32+977; cannot carry again
-  fe_canon(r);
-#endif
   return r;
 }
 __device__ __forceinline__ fe fp_reduce512(const u32 t[16]) { return fp_reduce512_t<0>(t); }
@@ -367,6 +369,13 @@ __device__ __forceinline__ fe fe_mul(const fe &a, const fe &b) {
   u32 t[16];
   fp_mul_wide(t, a, b);
   return fp_reduce512(t);
+}
+// canonical a * b / a^2 with the branch-free correction whatever ECL_FE_BRANCHFREE says: K2a (kernels.cuh) is bound by the
+// latency of the carry chains, and only products inside one basic block can overlap
+__device__ __forceinline__ fe fe_mul_bf(const fe &a, const fe &b) {
+  u32 t[16];
+  fp_mul_wide(t, a, b);
+  return fp_reduce512_t<2>(t);
 }
 // a * b as ANY representative of the residue below 2^256 (possibly >= p, with probability 2^-192): for products that only
 // feed further multiplications (which accept any 256-bit operand). Saves the canonical correction where the
@@ -513,6 +522,12 @@ __device__ __forceinline__ fe fe_sqr(const fe &a) {
 #else
   return fe_mul(a, a);
 #endif
+}
+
+__device__ __forceinline__ fe fe_sqr_bf(const fe &a) {
+  u32 t[16];
+  fp_sqr_wide(t, a);
+  return fp_reduce512_t<2>(t);
 }
 
 static __device__ __noinline__ fe fe_sqr_n(fe x, int n) {

@@ -85,6 +85,16 @@ __device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_f
 // calls fe_mul out of line through memory: fine for 75 000 centres per launch, 40 % of the time here).
 // The first non-zero window is a load; the second is an affine + affine addition (4M + 2S); the rest are mixed
 // additions (8M + 3S). Returns false for k = 0 (mod n).
+#ifndef ECL_MULPTS_BF
+#define ECL_MULPTS_BF 1  // K2a's products use the branch-free correction: independent products of an addition overlap
+#endif
+#if ECL_MULPTS_BF
+#define FE_MUL_K2 fe_mul_bf
+#define FE_SQR_K2 fe_sqr_bf
+#else
+#define FE_MUL_K2 fe_mul
+#define FE_SQR_K2 fe_sqr
+#endif
 static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
   int have = 0, dead = 0;  // dead: the sum hit infinity (k = 0 mod n); the loop still runs to its end (lockstep barriers)
   u32 dig[GTAB_WINDOWS];
@@ -106,17 +116,17 @@ static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const u
     }
     // mixed addition; with Z1 = 1 the first three products are copies, kept in one code path by multiplying by one:
     // the second window is 1 of 15 additions, a separate body would double the loop for a 3 % gain
-    const fe z2 = fe_sqr(acc.z);
-    const fe u2 = fe_mul(qx, z2);
-    const fe s2 = fe_mul(fe_mul(qy, z2), acc.z);
+    const fe z2 = FE_SQR_K2(acc.z);
+    const fe u2 = FE_MUL_K2(qx, z2);
+    const fe s2 = FE_MUL_K2(FE_MUL_K2(qy, z2), acc.z);
     const fe h = fe_sub(u2, acc.x);
     const fe rr = fe_sub(s2, acc.y);
-    const fe h2 = fe_sqr(h);
-    const fe h3 = fe_mul(h2, h);
-    const fe v = fe_mul(acc.x, h2);
-    const fe x3 = fe_sub(fe_sub(fe_sub(fe_sqr(rr), h3), v), v);
-    const fe y3 = fe_sub(fe_mul(rr, fe_sub(v, x3)), fe_mul(acc.y, h3));
-    const fe z3 = fe_mul(acc.z, h);
+    const fe h2 = FE_SQR_K2(h);
+    const fe h3 = FE_MUL_K2(h2, h);
+    const fe v = FE_MUL_K2(acc.x, h2);
+    const fe x3 = fe_sub(fe_sub(fe_sub(FE_SQR_K2(rr), h3), v), v);
+    const fe y3 = fe_sub(FE_MUL_K2(rr, fe_sub(v, x3)), FE_MUL_K2(acc.y, h3));
+    const fe z3 = FE_MUL_K2(acc.z, h);
     if (fe_is_zero(z3)) dead = 1;  // k = n lands on -acc at the top window: infinity
     acc.x = x3, acc.y = y3, acc.z = z3;
   }
@@ -155,18 +165,18 @@ __global__ void __launch_bounds__(256, ECL_MULPTS_MINBLOCKS) mul_points_kernel(c
     if (!ok) a.x = fe_zero(), a.y = fe_zero(), a.z = fe_one();
     uint4 *slot = scr + (size_t)m * 8 * T;
     if (store) st_fe(slot, T, a.x), st_fe(slot + 2 * T, T, a.y), st_fe(slot + 4 * T, T, a.z), st_fe(slot + 6 * T, T, acc);
-    acc = fe_mul(acc, a.z);
+    acc = FE_MUL_K2(acc, a.z);
   }
   fe inv = fe_inv(acc);
 #pragma unroll 1
   for (int m = (int)p.B - 1; m >= 0; --m) {
     uint4 *slot = scr + (size_t)m * 8 * T;
     const fe z = ld_fe(slot + 4 * T, T), pre = ld_fe(slot + 6 * T, T);
-    const fe zi = fe_mul(inv, pre);
-    inv = fe_mul(inv, z);
+    const fe zi = FE_MUL_K2(inv, pre);
+    inv = FE_MUL_K2(inv, z);
     const fe ax = ld_fe(slot, T), ay = ld_fe(slot + 2 * T, T);
-    const fe zi2 = fe_sqr(zi);
-    const fe fx = fe_mul(ax, zi2), fy = fe_mul(ay, fe_mul(zi2, zi));  // (0, 0) stays (0, 0): "no point for this key"
+    const fe zi2 = FE_SQR_K2(zi);
+    const fe fx = FE_MUL_K2(ax, zi2), fy = FE_MUL_K2(ay, FE_MUL_K2(zi2, zi));  // (0, 0) stays (0, 0): "no point for this key"
     if (store) st_fe(slot, T, fx), st_fe(slot + 2 * T, T, fy);
   }
 }

@@ -72,3 +72,42 @@ def test_large_batch_linearity(env):
     dev.set_filter(allones.bits)
     b = dev.batch_add(start, n, E.A33, cap=n)
     assert [(f.pk - start, f.h160) for f in a] == [(k, h) for k, _, _, h in b]
+
+
+def test_two_submits_in_flight_come_back_in_order(env):
+    """ECL_MUL_DEPTH submits may be pending; ecl_collect returns them in submission order with their own key indices; a
+    third submit is refused (ECL_E_STATE) and leaves the queue intact"""
+    E, H, dev = env
+    allones = H.Filter(np.full(1, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64), None)
+    dev.set_filter(allones.bits)
+    a = [2**200 + i for i in range(3000)]
+    b = [2**90 + 7 * i for i in range(5000)]
+    dev.mul_submit(a, E.A33)
+    dev.mul_submit(b, E.A33 | E.A65)
+    with pytest.raises(E.EclError) as ei:
+        dev.mul_submit(a, E.A33)
+    assert ei.value.code == -5
+    hits_a, n_a = dev.collect(cap=1 << 14)
+    hits_b, n_b = dev.collect(cap=1 << 14)
+    assert (n_a, n_b) == (3000, 5000)
+    assert [k for k, _, _, _ in hits_a] == list(range(3000))
+    assert [(k, kd) for k, _, kd, _ in hits_b] == [(i, kd) for i in range(5000) for kd in (0, 1)]
+    # the same hashes as one submit each
+    assert hits_a == dev.mul_batch(a, E.A33, cap=1 << 14)
+    assert hits_b == dev.mul_batch(b, E.A33 | E.A65, cap=1 << 14)
+    with pytest.raises(E.EclError):
+        dev.collect()
+
+
+def test_keys_spanning_every_window_digit(env):
+    """scalars that exercise the W-bit window boundaries of the table (all-ones, single bits, digits of 1 and 2^W - 1,
+    n - 1, n + 1, 2^256 - 1) against the oracle's double-and-add"""
+    import oracle as O
+
+    E, H, dev = env
+    ks = [1, 2, 3, 2**24 - 1, 2**24, 2**24 + 1, 2**48 - 1, 2**240, 2**240 - 1, 2**255, 2**256 - 1, O.N_ORDER - 1, O.N_ORDER + 1,
+          O.N_ORDER - 2**24, int("01" * 128, 2), int("10" * 128, 2)] + [1 << b for b in range(0, 256, 7)] + [(1 << b) - 1 for b in range(20, 256, 11)]
+    got = dev.scalar_mul(ks)
+    for k, (x, y) in zip(ks, got):
+        want = O.ec_mul_g(k % O.N_ORDER)
+        assert (x, y) == (want if want else (0, 0)), hex(k)
