@@ -95,15 +95,29 @@ __device__ __forceinline__ fe ld_fe(const uint4 *p, size_t stride) { return fe_f
 #define FE_MUL_K2 fe_mul
 #define FE_SQR_K2 fe_sqr
 #endif
+#ifndef ECL_MULPTS_PREFETCH
+#define ECL_MULPTS_PREFETCH 1
+#endif
+__device__ __forceinline__ void gtab_prefetch(const uint4 *gtab, u32 entry) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gtab + (size_t)entry * 4));
+}
 static __device__ __noinline__ bool gtab_mul_fast(jac &acc, const fe &k, const uint4 *__restrict__ gtab) {
   int have = 0, dead = 0;  // dead: the sum hit infinity (k = 0 mod n); the loop still runs to its end (lockstep barriers)
   u32 dig[GTAB_WINDOWS];
 #pragma unroll
   for (int w = 0; w < GTAB_WINDOWS; ++w) dig[w] = gtab_digit(k, w);
+#if ECL_MULPTS_PREFETCH
+  if (dig[0]) gtab_prefetch(gtab, dig[0] - 1);
+#endif
 #pragma unroll 1
   for (int w = 0; w < GTAB_WINDOWS; ++w) {
 #if ECL_MULPTS_SYNC
     __syncthreads();
+#endif
+#if ECL_MULPTS_PREFETCH
+    // the table is far larger than L2: the next window's entry is on its way from HBM while this window's addition
+    // (~2000 instructions) runs; a prefetch costs no register
+    if (w + 1 < GTAB_WINDOWS && dig[w + 1]) gtab_prefetch(gtab, (u32)(w + 1) * GTAB_STRIDE + dig[w + 1] - 1);
 #endif
     const u32 d = dig[w];
     if (d == 0 || dead) continue;
