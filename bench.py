@@ -239,6 +239,12 @@ ENDO_EXTRA_OPS = 2400  # each extra endomorphism image (hash160_33 + 
 RANGE71_S, RANGE71_E = 0x400000000000000000, 0x7FFFFFFFFFFFFFFFFF  # Makefile:58 (range_71)
 
 
+def shard71_of(rank: int, world: int):
+    """contiguous job-aligned shard [start, start + n_keys) of 400000000000000000:7fffffffffffffffff (Makefile:58) for `rank`"""
+    per = (RANGE71_E - RANGE71_S) // world // (1 << 21) * (1 << 21)
+    return RANGE71_S + rank * per, per
+
+
 def _allreduce(world, local, vals, op):
     import torch
     import torch.distributed as dist
@@ -367,9 +373,7 @@ def leg_endo_blf(E, H, dev, rank, world, local, peaks, size_words, log2_step, st
     import torch
     import torch.distributed as dist
 
-    total = RANGE71_E - RANGE71_S
-    per = total // world // (1 << 21) * (1 << 21)
-    shard = RANGE71_S + rank * per
+    shard, _ = shard71_of(rank, world)
     step_keys = 1 << log2_step
     r = __import__("random").Random(4 + rank)
     planted = sorted(r.randrange((steps + 1) * step_keys) for _ in range(6))

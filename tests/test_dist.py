@@ -25,6 +25,21 @@ def test_shards_partition_the_range():
         assert sum(n for _, n in shards) == bench.RANGE_KEYS
 
 
+def test_config4_shards_are_job_aligned_and_disjoint():
+    """BASELINE configs[3]: the range of Makefile:58 cut into one shard per GPU (bench.py's add_endo_blf leg)"""
+    import bench
+
+    for world in (1, 2, 4, 8):
+        shards = [bench.shard71_of(r, world) for r in range(world)]
+        assert shards[0][0] == 0x400000000000000000
+        for (s0, n0), (s1, _) in zip(shards, shards[1:]):
+            assert s0 + n0 == s1 and n0 % (1 << 21) == 0
+        last_s, last_n = shards[-1]
+        assert last_s + last_n <= 0x7FFFFFFFFFFFFFFFFF and 0x7FFFFFFFFFFFFFFFFF - (last_s + last_n) < world << 21
+        # every rank's timed prefix (3 steps of 2^32 keys) lies inside its own shard
+        assert all(n > 3 << 32 for _, n in shards)
+
+
 def _worker(rank, world, port, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
