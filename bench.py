@@ -310,23 +310,28 @@ def leg_mul(E, H, dev, rank, world, local, peaks, n_keys, with_reference):
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    reps = 30  # the 10 M keys take ~35 ms: repeated so that the clock sampler (200 ms period) sees the leg under load
     t0 = time.perf_counter()
-    found, hot_ms = run_all()
+    hot_ms, ok = 0.0, True
+    for _ in range(reps):
+        found, h_ms = run_all()
+        hot_ms += h_ms
+        ok = ok and sorted(found) == sorted(want)
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop()
-    ok = sorted(found) == sorted(want)
     wall_ms, hot_ms = _allreduce(world, local, [wall_ms, hot_ms], "MAX")
     ok = _allreduce(world, local, [1.0 if ok else 0.0], "MIN")[0] == 1.0
     if rank != 0:
         return None, ok
-    kern = n_keys / (hot_ms * 1e-3) / 1e6  # per GPU (max rank)
-    e2e = n_keys * world / (wall_ms * 1e-3) / 1e6
+    kern = n_keys * reps / (hot_ms * 1e-3) / 1e6  # per GPU (max rank)
+    e2e = n_keys * reps * world / (wall_ms * 1e-3) / 1e6
     B = max(1, -(-batch // (148 * 512)))
     field_mults = 10 * 11 + 7 + 270.0 / B  # W = 24: 11 windows, the first is a load
     ops = field_mults * 45 + 10 * 8 * 16 + (CU_OPS_PER_KEY - 321)  # canonical ALU-pipe ops: 45 per multiplication
     alu_peak = peaks["lop3_gops"] * 1e9
     leg = {
-        "workload": f"mul: {n_keys} seeded 256-bit keys per GPU from host memory, -a cu (BASELINE configs[2]), batches of 2^22, {E.MUL_DEPTH} submits in flight",
+        "workload": f"mul: {n_keys} seeded 256-bit keys per GPU from host memory, -a cu (BASELINE configs[2]), batches of 2^22, {E.MUL_DEPTH} submits in flight, "
+                    f"the pass over the {n_keys} keys repeated {reps}x inside the timed region",
         "metric": "Mkeys/s (mul mode, -a cu)", "unit": "Mkeys/s", "n_gpus": world,
         "value": round(kern * world, 2), "value_note": "mul_points_kernel + mul_hash_kernel, CUDA events on the launch stream, max over ranks, x n_gpus",
         "e2e": {"value": round(e2e, 2), "unit": "Mkeys/s", "h2d_bytes_per_step": 32 * batch, "d2h_bytes_per_step": 4,
