@@ -591,11 +591,22 @@ def ours_arm(args):
     secondary, sec_ok = {}, True
     if not args.no_secondary:
         with_ref = world == 1 and not args.no_cpu_baseline
-        leg, ok2 = leg_mul(E, H, dev, rank, world, local, peaks_all(dev, peaks, world, local), args.mul_keys, with_ref)
-        secondary["mul_10M_cu"], sec_ok = leg, sec_ok and ok2
-        leg, ok2 = leg_endo_blf(E, H, dev, rank, world, local, peaks_all(dev, peaks, world, local), int(args.blf_gib * 2**30) // 8 - 5,
-                                args.endo_log2_step, args.endo_steps)
-        secondary["add_endo_blf"], sec_ok = leg, sec_ok and ok2
+        def guarded(name, fn):
+            """a leg that dies (out of memory on a shared box, a missing binary) must not take the headline line with it:
+            the error is recorded in its place; a leg that RUNS and fails its parity gate still fails the whole bench"""
+            nonlocal sec_ok
+            try:
+                leg, ok2 = fn()
+            except Exception as e:  # noqa: BLE001
+                leg, ok2 = {"error": f"{type(e).__name__}: {e}"[:500], "parity_gate": "not run to the end (the leg raised)"}, True
+            if leg is not None or rank == 0:
+                secondary[name] = leg
+            sec_ok = sec_ok and ok2
+
+        pk_all = peaks_all(dev, peaks, world, local)
+        guarded("mul_10M_cu", lambda: leg_mul(E, H, dev, rank, world, local, pk_all, args.mul_keys, with_ref))
+        guarded("add_endo_blf", lambda: leg_endo_blf(E, H, dev, rank, world, local, pk_all, int(args.blf_gib * 2**30) // 8 - 5,
+                                                     args.endo_log2_step, args.endo_steps))
         dev.close()  # the C host of the rnd leg opens the GPUs itself
         torch.cuda.synchronize()
         # the other ranks wait on the CPU (gloo): an NCCL barrier is a kernel spinning on their GPUs, which the C host needs
@@ -603,8 +614,7 @@ def ours_arm(args):
         if world > 1:
             dist.barrier(group=cpu_group)
         if rank == 0 and args.rnd_windows > 0:
-            leg, ok2 = leg_rnd(world, args.rnd_windows, with_ref)
-            secondary["rnd_128_32_cu"], sec_ok = leg, sec_ok and ok2
+            guarded("rnd_128_32_cu", lambda: leg_rnd(world, args.rnd_windows, with_ref))
         if world > 1:
             dist.barrier(group=cpu_group)
     ok = ok and sec_ok
