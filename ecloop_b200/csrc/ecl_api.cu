@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "filter_kernels.cuh"
+#include "launch_plan.h"
 #include "kernels.cuh"
 #include "peak.cuh"
 
@@ -545,25 +546,6 @@ static cudaEvent_t next_event(ecl_dev *dev) {
   return dev->ev_pool[dev->ev_used++];
 }
 
-// Launch geometry for `keys` consecutive keys: T threads walk c groups of 2*Hr keys each. The half group Hr is a
-// run-time quantity (table prefix (i+1)*s*G, i < Hr, plus the step 2*Hr*s*G), so instead of rounding the span up to
-// whole rounds of 148 x 512 threads x 2048 keys (a 2^32-key span left 1.2 % of the lanes idle in its tail launch,
-// a 2^29-key span 13 %), Hr is chosen so that T * c * 2*Hr covers the span within one group per thread.
-struct launch_plan {
-  u32 T, c, Hr;
-};
-static launch_plan plan_launch(u64 keys, u32 Tmax) {
-  const u64 full = (u64)Tmax * GROUP_KEYS;
-  const u64 c = (keys + full - 1) / full;
-  const u64 per_thread = (keys + Tmax - 1) / Tmax;
-  u64 Hr = (per_thread + 2 * c - 1) / (2 * c);
-  Hr = std::min<u64>(ADD_H, std::max<u64>(HR_MIN, Hr));
-  launch_plan lp;
-  lp.c = (u32)c, lp.Hr = (u32)Hr;
-  lp.T = (u32)((keys + c * 2 * Hr - 1) / (c * 2 * Hr));
-  return lp;
-}
-
 // Queue the launches covering keys [k_begin, k_end) of the pending span. max_keys_per_launch bounds one launch.
 static int launch_add(ecl_dev *dev, u64 k_begin, u64 k_end, u64 max_keys_per_launch, bool drain_each, std::vector<ecl_hit> *drain_to) {
   const u32 smem_table = (ADD_H + 1) * 64;
@@ -598,7 +580,7 @@ static int launch_add(ecl_dev *dev, u64 k_begin, u64 k_end, u64 max_keys_per_lau
     u32 threads = dev->Tmax;
     if (const char *env = getenv("ECLOOP_B200_MAX_THREADS"))  // test hook: few threads make small spans use large half groups
       threads = std::min<u32>(dev->Tmax, std::max<u32>(1u, (u32)strtoul(env, nullptr, 10)));
-    const launch_plan lp = plan_launch(L, threads);
+    const launch_plan lp = plan_launch(L, threads, ADD_H, HR_MIN);
     // centres: (start + (k + Hr + t*c*2Hr) * stride) * G   (GStart, main.c:359-360)
     u64 k0[4], step[4], kstep[4];
     const u64 zero[4] = {0, 0, 0, 0};

@@ -81,3 +81,14 @@ def test_resource_usage_of_the_hot_kernels():
         if "mul_points_kernel" in name:
             assert int(r) <= 128, (name, r)  # two CTAs of 256 threads per SM
     assert any("add_kernel_sp" in n for n in regs)
+
+
+def test_launch_planner_invariants(tmp_path):
+    """ecloop_b200/csrc/launch_plan.h on the CPU (tests/csrc/plan_test.cpp): every span size is covered, fits the resident
+    threads, overhangs by less than one thread's share, and the shapes quoted in DESIGN.md K1 come out"""
+    exe = tmp_path / "plan_test"
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-o", str(exe), str(ROOT / "tests" / "csrc" / "plan_test.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
