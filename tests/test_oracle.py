@@ -228,3 +228,55 @@ def test_dump_mul_raw(golden):
     keys = [int.from_bytes(hashlib.sha256(l.encode()).digest(), "big") for l in lines if l]
     n, hits = O.mul_batch(keys, O.A33 | O.A65, ALL)
     assert dump_lines(hits) == golden_lines("dump_mul_raw_8_cu")
+
+
+def test_blf_gen_mirror_against_the_reference_tool(tmp_path):
+    """oracle.blf_gen_sequential (what tests/test_gpu_filter.py holds ecl_filter_add to) against the unmodified reference's
+    own `blf-gen` (lib/utils.c:409-475): a small filter that saturates and an input with repeats, so that the
+    `if (blf_has) continue` branch decides the count; same "added N new items", same file bytes, create and update."""
+    import random
+    import re
+    import struct
+    import subprocess
+
+    exe = O.ref_binary()
+    if exe is None:
+        pytest.skip("oracle/_ref not built")
+    r = random.Random(11)
+    for n_arg, n_hashes in ((40, 400), (3000, 6000)):
+        hashes = []
+        for _ in range(n_hashes):
+            hashes.append(r.choice(hashes) if hashes and r.random() < 0.25 else tuple(r.getrandbits(32) for _ in range(5)))
+        half = n_hashes // 2
+        p = tmp_path / f"f{n_arg}.blf"
+        counts = []
+        for part in (hashes[:half], hashes[half:]):
+            text = "".join("%08x%08x%08x%08x%08x\n" % h for h in part).encode()
+            res = subprocess.run([str(exe), "blf-gen", "-n", str(n_arg), "-o", str(p)], input=text, capture_output=True, timeout=120)
+            assert res.returncode == 0, res.stderr
+            counts.append(int(re.search(rb"added ([\d,]+) new items", res.stdout).group(1).replace(b",", b"")))
+        raw = p.read_bytes()
+        magic, ver, size = struct.unpack("<IIQ", raw[:16])
+        assert (magic, ver) == (0x45434246, 1)
+        bits = [0] * size
+        want = [O.blf_gen_sequential(bits, hashes[:half]), O.blf_gen_sequential(bits, hashes[half:])]
+        assert counts == want
+        assert want[0] < half  # the small filter saturates / repeats are skipped: the order-dependent branch was taken
+        assert list(struct.unpack("<%dQ" % size, raw[16:])) == bits
+
+
+def test_synthetic_filter_statistics():
+    """the counter-based generator behind ecl_filter_generate (numpy mirror): fill = round(fill * 256) / 256 within sampling
+    error, bits of a word and of neighbouring words uncorrelated, reproducible, seed-sensitive"""
+    import numpy as np
+
+    a = O.synthetic_filter(1 << 14, 0.37, 4)
+    b = O.synthetic_filter(1 << 14, 0.37, 4)
+    c = O.synthetic_filter(1 << 14, 0.37, 5)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    ones = np.unpackbits(a.view(np.uint8)).astype(np.float64)
+    p = 95 / 256
+    assert abs(ones.mean() - p) < 4 * (p * (1 - p) / ones.size) ** 0.5
+    for lag in (1, 7, 8, 63, 64, 65):
+        cov = np.mean(ones[:-lag] * ones[lag:]) - p * p
+        assert abs(cov) < 5 * p * (1 - p) / ones.size ** 0.5, (lag, cov)
